@@ -1,0 +1,2 @@
+"""B200-native cut-selection hot path of rb2309/SDPCutSel-via-NN."""
+from . import nn_weights  # noqa: F401
