@@ -1,0 +1,158 @@
+/* libsdpcutsel -- C ABI of the B200 (sm_100a) cut-selection hot path.
+ *
+ * Drop-in boundary for the per-round selection path of rb2309/SDPCutSel-via-NN.  The reference has one
+ * FFI crossing on this path -- ctypes -> neural_nets/NNs.so: `double neural_net_{2..5}D(const double*)`
+ * (cut_select_qp.py:284-303, call sites 579-582) -- and otherwise a Python method surface
+ * (CutSolver._get_sdp_vertex_cover :377, ._sel_eigcut_by_ordering_on_measure :543,
+ * ._gen_eigcuts_selected :705, ._get_eigendecomp :788, .__preprocess_triangle_ineq :799,
+ * .__separate_and_add_triangle :823).  Each entry point below names the reference lines it replaces.
+ *
+ * Conventions: plain pointers and sizes only; all pointers are HOST pointers owned by the caller unless the
+ * name says `_dev`; arrays are C-contiguous; every function returns 0 (SDPCS_OK) or a negative error code
+ * and never throws; sdpcs_last_error() gives the message.  One context drives one GPU; calls on a context
+ * are serialised by the caller.  There is no CPU fallback: without a CUDA device sdpcs_create fails.
+ */
+#ifndef SDPCUTSEL_H
+#define SDPCUTSEL_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDPCS_OK 0
+#define SDPCS_ERR_INVALID (-1) /* bad argument */
+#define SDPCS_ERR_CUDA (-2)    /* CUDA runtime error (message in sdpcs_last_error) */
+#define SDPCS_ERR_STATE (-3)   /* weights / instance / cover / scores not set */
+#define SDPCS_ERR_NOMEM (-4)   /* shard does not fit in device memory */
+
+#define SDPCS_MAX_N 250 /* north_star: n <= 250 */
+#define SDPCS_MAX_RHO 5
+
+/* selection strategies, numbering of cut_select_qp.py:80-81 */
+#define SDPCS_STRAT_FEAS 1
+#define SDPCS_STRAT_OPT 2
+#define SDPCS_STRAT_COMB 4
+
+typedef struct sdpcs_ctx sdpcs_ctx;
+
+/* Algorithmic constants, mirrors the class attributes at cut_select_qp.py:22-41. */
+typedef struct sdpcs_params {
+    double thres_min_opt;    /* _THRES_MIN_OPT    = 0      */
+    double thres_neg_eigval; /* _THRES_NEG_EIGVAL = -1e-15 */
+    double big_m;            /* _BIG_M            = 1000   */
+    double thres_tri_viol;   /* _THRES_TRI_VIOL   = 1e-7   */
+    int32_t thres_tri_dense; /* _THRES_TRI_DENSE  = 2      */
+    int32_t jacobi_sweeps;   /* 0 = built-in default per matrix order */
+} sdpcs_params;
+
+/* Device timings (ms, CUDA events on the context's stream) of the last sdpcs_score / sdpcs_topk calls. */
+typedef struct sdpcs_timings {
+    double score_ms;      /* fused unrank+gather+eig(+NN) kernels                      */
+    double select_ms;     /* key build + radix select + collect + sort                 */
+    double h2d_ms;        /* upload of vars_values                                      */
+    int64_t score_launches;
+    int64_t select_launches;
+} sdpcs_timings;
+
+int sdpcs_default_params(sdpcs_params *p);
+int sdpcs_create(sdpcs_ctx **out, int device);
+int sdpcs_destroy(sdpcs_ctx *ctx);
+const char *sdpcs_last_error(const sdpcs_ctx *ctx); /* ctx may be NULL: last creation error */
+int sdpcs_set_stream(sdpcs_ctx *ctx, void *cuda_stream); /* cudaStream_t; NULL = context-owned stream */
+int sdpcs_set_params(sdpcs_ctx *ctx, const sdpcs_params *p);
+int sdpcs_get_timings(const sdpcs_ctx *ctx, sdpcs_timings *t);
+
+/* NN_rhoD weights, rho in 2..5; blob layout in sdpcutsel-via-nn_b200/nn_weights.py.
+ * Replaces ctypes.cdll.LoadLibrary('neural_nets/NNs.so') + getattr(lib, 'neural_net_%dD')
+ * (cut_select_qp.py:297-303). */
+int sdpcs_set_weights(sdpcs_ctx *ctx, int rho, const double *blob, int64_t len);
+
+/* Instance arrays: Q_arr = upper triangle of Q, row-major, n(n+1)/2 doubles (cut_select_qp.py:318-321,
+ * cut_select_qcqp.py:259).  Invalidates cover and scores. */
+int sdpcs_set_instance(sdpcs_ctx *ctx, int n, const double *Q_arr);
+
+/* Candidate set = all rho-subsets with lexicographic rank in [rank_begin, rank_end) (rank_end < 0: C(n,rho)).
+ * Candidate index (agg_idx) == lex rank.  Nothing is stored: subsets are unranked on the fly.
+ * Replaces the nested loops at cut_select_qp.py:451-455 and the aggregation at 524-540. */
+int sdpcs_set_cover_all(sdpcs_ctx *ctx, int rho, int64_t rank_begin, int64_t rank_end);
+
+/* Candidate set = explicit list (pattern-E vertex cover, cut_select_qp.py:401-522): idx is N x rho int16,
+ * rows padded with -1 for cliques smaller than rho (sizes 2..rho may be mixed); candidate i has
+ * agg_idx = agg_offset + i. */
+int sdpcs_set_cover_list(sdpcs_ctx *ctx, int rho, const int16_t *idx, int64_t N, int64_t agg_offset);
+
+int sdpcs_num_candidates(const sdpcs_ctx *ctx, int64_t *N);
+
+/* Score every candidate of the cover at the LP point vars_values = [X upper-tri row-major | x]
+ * (cut_select_qp.py:547).  want bit 0: lam_min of [1 x^T; x X]_rho (cut_select_qp.py:643-647, 788-797);
+ * bit 1: optimality measure max_elem*(NN(x_rho, Q~_rho) - <Q~_rho, X_rho>) (cut_select_qp.py:573-582).
+ * Scores stay resident on the device for sdpcs_topk / sdpcs_scores. */
+int sdpcs_score(sdpcs_ctx *ctx, const double *vars_values, int want);
+
+/* Copy resident scores of local candidates [i0, i1) to the host (either pointer may be NULL). Parity tests. */
+int sdpcs_scores(sdpcs_ctx *ctx, int64_t i0, int64_t i1, double *out_lam, double *out_obj);
+
+/* Counters over the resident scores: out[0] = N, out[1] = #violated (lam < thres_neg_eigval),
+ * out[2] = #strong (obj > thres_min_opt and violated).  (cut_select_qp.py:604-615, 629) */
+int sdpcs_counts(sdpcs_ctx *ctx, int64_t *out3);
+
+/* Top-k of the resident scores.  mode:
+ *   1  feasibility: violated only, key -lam desc, ties agg_idx asc          (cut_select_qp.py:639-654)
+ *   2  optimality:  all, key obj desc, ties agg_idx asc                      (cut_select_qp.py:599-601)
+ *   3  strong set:  obj > thres_min_opt and violated, key obj desc           (cut_select_qp.py:607-612)
+ *   4  combined final: key = re-scored measure of cut_select_qp.py:603-625 given the pivot
+ *      (pivot_obj, pivot_idx = the k-th strong candidate, all_walked = |S| < k), ties by (obj desc, agg_idx asc)
+ * Outputs (length k, first *out_n valid, already in final order): agg_idx, key score, lam, obj. */
+int sdpcs_topk(sdpcs_ctx *ctx, int mode, int64_t k, double pivot_obj, int64_t pivot_idx, int all_walked,
+               int64_t *out_idx, double *out_score, double *out_lam, double *out_obj, int64_t *out_n);
+
+/* Merge m entries gathered from several shards into the global top-k with the same comparator
+ * (score desc, obj2 desc, agg_idx asc); perm receives the positions of the winners, in order. */
+int sdpcs_merge_topk(sdpcs_ctx *ctx, int64_t m, const double *score, const double *obj2, const int64_t *idx,
+                     int64_t k, int64_t *out_perm, int64_t *out_n);
+
+/* One-call selection on a single GPU with HOST buffers (upload + score + select + download):
+ * the whole of _sel_eigcut_by_ordering_on_measure (cut_select_qp.py:543-654) for strat 1, 2, 4, returning the
+ * prefix of length <= k of the ranked list.  out_counts = {N, #violated walked, #strong}; out_new_strat as
+ * cut_select_qp.py:629 (strat 4 only, else = strat). */
+int sdpcs_select(sdpcs_ctx *ctx, int strat, const double *vars_values, int64_t k,
+                 int64_t *out_idx, double *out_score, double *out_lam, double *out_obj,
+                 int64_t *out_n, int64_t *out_counts, int *out_new_strat);
+
+/* Lexicographic unranking (host utility, no GPU): ranks[m] -> out_idx[m x rho]. */
+int sdpcs_unrank(int n, int rho, const int64_t *ranks, int64_t m, int32_t *out_idx);
+int sdpcs_binom(int n, int k, int64_t *out);
+
+/* Eigenvector cuts for m selected subsets (cut_select_qp.py:737-751): sets is m x rho int16 (-1 padded).
+ * width = rho + rho(rho+1)/2.  out_ind (m x width, -1 padded): LP columns [x vars | X vars];
+ * out_val: coefficients; out_rhs = -v0^2; out_lam: lam_min (eigh); out_violated: lam < thres_neg_eigval. */
+int sdpcs_gen_cuts(sdpcs_ctx *ctx, int rho, const int16_t *sets, int64_t m, const double *vars_values,
+                   int64_t *out_ind, double *out_val, double *out_rhs, double *out_lam, uint8_t *out_violated);
+
+/* Eigen-decomposition of one [1 x^T; x X] matrix of order d+1 (cut_select_qp.py:788-797): eigenvalues
+ * ascending, eigenvectors as columns of V (row-major (d+1)x(d+1)); out_vecs may be NULL. */
+int sdpcs_eigendecomp(sdpcs_ctx *ctx, int d, const double *curr_pt, const double *X_slice,
+                      double *out_vals, double *out_vecs);
+
+/* Triangle inequalities (cut_select_qp.py:799-863).  adj: n x n uint8 sparsity pattern (NULL = dense).
+ * sdpcs_triangles scores all triples with >= thres_tri_dense edges, keeps violations >= thres_tri_viol,
+ * orders by (density, violation) desc with ties in (triple lex rank, type) order, and returns the first
+ * min(kmax, #violated): lex rank of the triple, type 0..3, violation, density; *out_n_violated = #violated. */
+int sdpcs_set_tri_pattern(sdpcs_ctx *ctx, const uint8_t *adj);
+int sdpcs_triangles(sdpcs_ctx *ctx, const double *vars_values, int64_t kmax, int64_t *out_triple_rank,
+                    int8_t *out_type, double *out_viol, int8_t *out_density, int64_t *out_n,
+                    int64_t *out_n_violated, int64_t *out_n_triples);
+
+/* Batched NN_rhoD forward pass on the GPU for m input rows of length rho(rho+3)/2 -- the replacement of
+ * `neural_net_%dD(input_arr)` (cut_select_qp.py:579-582). */
+int sdpcs_nn_eval(sdpcs_ctx *ctx, int rho, const double *inputs, int64_t m, double *out);
+
+/* FP64 roofline denominators measured on this device: DFMA and DMMA.8x8x4 peak TFLOP/s. */
+int sdpcs_fp64_peak(sdpcs_ctx *ctx, double *dfma_tflops, double *dmma_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,257 @@
+"""ctypes binding of libsdpcutsel.so (include/sdpcutsel.h). No torch types cross this boundary.
+
+The library is the only compute path: if it is missing or no sm_100a device is present, construction
+raises -- there is no CPU fallback.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libsdpcutsel.so")
+
+c_i64, c_dbl, c_int, c_vp = ctypes.c_int64, ctypes.c_double, ctypes.c_int, ctypes.c_void_p
+P = ctypes.POINTER
+
+EXPORTS = [
+    "sdpcs_default_params", "sdpcs_create", "sdpcs_destroy", "sdpcs_last_error", "sdpcs_set_stream", "sdpcs_set_params",
+    "sdpcs_get_timings", "sdpcs_set_weights", "sdpcs_set_instance", "sdpcs_set_cover_all", "sdpcs_set_cover_list",
+    "sdpcs_num_candidates", "sdpcs_score", "sdpcs_scores", "sdpcs_counts", "sdpcs_topk", "sdpcs_merge_topk",
+    "sdpcs_select", "sdpcs_unrank", "sdpcs_binom", "sdpcs_gen_cuts", "sdpcs_eigendecomp", "sdpcs_set_tri_pattern",
+    "sdpcs_triangles", "sdpcs_nn_eval", "sdpcs_fp64_peak",
+]
+
+
+class Params(ctypes.Structure):
+    _fields_ = [("thres_min_opt", c_dbl), ("thres_neg_eigval", c_dbl), ("big_m", c_dbl), ("thres_tri_viol", c_dbl),
+                ("thres_tri_dense", ctypes.c_int32), ("jacobi_sweeps", ctypes.c_int32)]
+
+
+class Timings(ctypes.Structure):
+    _fields_ = [("score_ms", c_dbl), ("select_ms", c_dbl), ("h2d_ms", c_dbl), ("score_launches", c_i64),
+                ("select_launches", c_i64)]
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """dlopen libsdpcutsel.so (built in-tree by build.py); raises if it is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise RuntimeError("libsdpcutsel.so not found at %s: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(the CUDA library is the only compute path; there is no CPU fallback)" % path)
+    lib = ctypes.CDLL(path)
+    lib.sdpcs_last_error.restype = ctypes.c_char_p
+    lib.sdpcs_last_error.argtypes = [c_vp]
+    for name in EXPORTS:
+        if name != "sdpcs_last_error":
+            getattr(lib, name).restype = c_int
+    _lib = lib
+    return lib
+
+
+class SdpcsError(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(c_vp)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Engine(object):
+    """One GPU context of libsdpcutsel (one per process / per cover)."""
+
+    def __init__(self, device=0):
+        self._lib = load_library()
+        self._ctx = c_vp()
+        rc = self._lib.sdpcs_create(ctypes.byref(self._ctx), c_int(device))
+        if rc != 0:
+            msg = self._lib.sdpcs_last_error(None)
+            self._ctx = None
+            raise SdpcsError("sdpcs_create failed (%d): %s" % (rc, msg.decode() if msg else ""))
+        self.n = 0
+        self.rho = 0
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.sdpcs_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            msg = self._lib.sdpcs_last_error(self._ctx)
+            raise SdpcsError("libsdpcutsel error %d: %s" % (rc, msg.decode() if msg else ""))
+
+    # -- setup -------------------------------------------------------------------------------------
+    def set_stream(self, stream_ptr):
+        self._ck(self._lib.sdpcs_set_stream(self._ctx, c_vp(stream_ptr)))
+
+    def set_params(self, **kw):
+        p = Params()
+        self._lib.sdpcs_default_params(ctypes.byref(p))
+        for k, v in kw.items():
+            setattr(p, k, v)
+        self._ck(self._lib.sdpcs_set_params(self._ctx, ctypes.byref(p)))
+
+    def set_weights(self, rho, blob):
+        blob = _f64(blob)
+        self._ck(self._lib.sdpcs_set_weights(self._ctx, c_int(rho), _ptr(blob), c_i64(blob.size)))
+
+    def set_instance(self, n, Q_arr):
+        Q_arr = _f64(Q_arr)
+        if Q_arr.size != n * (n + 1) // 2:
+            raise ValueError("Q_arr must hold n(n+1)/2 values")
+        self._ck(self._lib.sdpcs_set_instance(self._ctx, c_int(n), _ptr(Q_arr)))
+        self.n = n
+
+    def set_cover_all(self, rho, rank_begin=0, rank_end=-1):
+        self._ck(self._lib.sdpcs_set_cover_all(self._ctx, c_int(rho), c_i64(rank_begin), c_i64(rank_end)))
+        self.rho = rho
+
+    def set_cover_list(self, rho, idx, agg_offset=0):
+        idx = np.ascontiguousarray(idx, dtype=np.int16).reshape(-1, rho)
+        self._ck(self._lib.sdpcs_set_cover_list(self._ctx, c_int(rho), _ptr(idx), c_i64(idx.shape[0]), c_i64(agg_offset)))
+        self.rho = rho
+
+    @property
+    def num_candidates(self):
+        N = c_i64()
+        self._ck(self._lib.sdpcs_num_candidates(self._ctx, ctypes.byref(N)))
+        return N.value
+
+    # -- scoring / selection -----------------------------------------------------------------------
+    def score(self, vars_values, want=3):
+        v = _f64(vars_values)
+        if v.size != self.n * (self.n + 1) // 2 + self.n:
+            raise ValueError("vars_values must hold n(n+1)/2 + n values")
+        self._ck(self._lib.sdpcs_score(self._ctx, _ptr(v), c_int(want)))
+
+    def scores(self, i0=0, i1=None, lam=True, obj=True):
+        i1 = self.num_candidates if i1 is None else i1
+        ol = np.empty(i1 - i0) if lam else None
+        oo = np.empty(i1 - i0) if obj else None
+        self._ck(self._lib.sdpcs_scores(self._ctx, c_i64(i0), c_i64(i1), _ptr(ol), _ptr(oo)))
+        return ol, oo
+
+    def counts(self):
+        out = np.zeros(3, dtype=np.int64)
+        self._ck(self._lib.sdpcs_counts(self._ctx, _ptr(out)))
+        return out
+
+    def topk(self, mode, k, pivot_obj=0.0, pivot_idx=0, all_walked=0):
+        k = int(k)
+        kk = max(k, 1)
+        idx, sc, lam, obj = np.empty(kk, np.int64), np.empty(kk), np.empty(kk), np.empty(kk)
+        n = c_i64()
+        self._ck(self._lib.sdpcs_topk(self._ctx, c_int(mode), c_i64(k), c_dbl(pivot_obj), c_i64(pivot_idx), c_int(all_walked),
+                                      _ptr(idx), _ptr(sc), _ptr(lam), _ptr(obj), ctypes.byref(n)))
+        m = n.value
+        return idx[:m], sc[:m], lam[:m], obj[:m]
+
+    def merge_topk(self, score, obj2, idx, k):
+        score, idx = _f64(score), np.ascontiguousarray(idx, dtype=np.int64)
+        obj2 = None if obj2 is None else _f64(obj2)
+        perm = np.empty(max(min(k, score.size), 1), np.int64)
+        n = c_i64()
+        self._ck(self._lib.sdpcs_merge_topk(self._ctx, c_i64(score.size), _ptr(score), _ptr(obj2), _ptr(idx), c_i64(k),
+                                            _ptr(perm), ctypes.byref(n)))
+        return perm[:n.value]
+
+    def select(self, strat, vars_values, k):
+        """One-call selection with host buffers. Returns dict(idx, score, lam, obj, counts, new_strat)."""
+        v = _f64(vars_values)
+        if v.size != self.n * (self.n + 1) // 2 + self.n:
+            raise ValueError("vars_values must hold n(n+1)/2 + n values")
+        k = int(k)
+        kk = max(k, 1)
+        idx, sc, lam, obj = np.empty(kk, np.int64), np.empty(kk), np.empty(kk), np.empty(kk)
+        n, ns = c_i64(), c_int()
+        counts = np.zeros(3, dtype=np.int64)
+        self._ck(self._lib.sdpcs_select(self._ctx, c_int(strat), _ptr(v), c_i64(k), _ptr(idx), _ptr(sc), _ptr(lam), _ptr(obj),
+                                        ctypes.byref(n), _ptr(counts), ctypes.byref(ns)))
+        m = n.value
+        return dict(idx=idx[:m], score=sc[:m], lam=lam[:m], obj=obj[:m], counts=counts, new_strat=ns.value)
+
+    def timings(self):
+        t = Timings()
+        self._ck(self._lib.sdpcs_get_timings(self._ctx, ctypes.byref(t)))
+        return dict(score_ms=t.score_ms, select_ms=t.select_ms, h2d_ms=t.h2d_ms, score_launches=t.score_launches,
+                    select_launches=t.select_launches)
+
+    # -- cuts / eig / triangles / nn ---------------------------------------------------------------
+    def gen_cuts(self, rho, sets, vars_values):
+        sets = np.ascontiguousarray(sets, dtype=np.int16).reshape(-1, rho)
+        m = sets.shape[0]
+        width = rho + rho * (rho + 1) // 2
+        ind, val = np.empty((m, width), np.int64), np.empty((m, width))
+        rhs, lam, viol = np.empty(m), np.empty(m), np.empty(m, np.uint8)
+        v = _f64(vars_values)
+        self._ck(self._lib.sdpcs_gen_cuts(self._ctx, c_int(rho), _ptr(sets), c_i64(m), _ptr(v), _ptr(ind), _ptr(val), _ptr(rhs),
+                                          _ptr(lam), _ptr(viol)))
+        return ind, val, rhs, lam, viol.astype(bool)
+
+    def eigendecomp(self, d, curr_pt, X_slice, want_vecs=True):
+        pt, Xs = _f64(curr_pt), _f64(X_slice)
+        vals = np.empty(d + 1)
+        vecs = np.empty((d + 1, d + 1)) if want_vecs else None
+        self._ck(self._lib.sdpcs_eigendecomp(self._ctx, c_int(d), _ptr(pt), _ptr(Xs), _ptr(vals), _ptr(vecs)))
+        return vals, vecs
+
+    def set_tri_pattern(self, adj):
+        a = None if adj is None else np.ascontiguousarray(adj, dtype=np.uint8)
+        self._ck(self._lib.sdpcs_set_tri_pattern(self._ctx, _ptr(a)))
+
+    def triangles(self, vars_values, kmax):
+        v = _f64(vars_values)
+        kk = max(int(kmax), 1)
+        rank, typ, viol, dens = np.empty(kk, np.int64), np.empty(kk, np.int8), np.empty(kk), np.empty(kk, np.int8)
+        n, nv, nt = c_i64(), c_i64(), c_i64()
+        self._ck(self._lib.sdpcs_triangles(self._ctx, _ptr(v), c_i64(int(kmax)), _ptr(rank), _ptr(typ), _ptr(viol), _ptr(dens),
+                                           ctypes.byref(n), ctypes.byref(nv), ctypes.byref(nt)))
+        m = n.value
+        return dict(rank=rank[:m], type=typ[:m], viol=viol[:m], density=dens[:m], n_violated=nv.value, n_triples=nt.value)
+
+    def nn_eval(self, rho, inputs):
+        x = _f64(inputs).reshape(-1, rho * (rho + 3) // 2)
+        out = np.empty(x.shape[0])
+        self._ck(self._lib.sdpcs_nn_eval(self._ctx, c_int(rho), _ptr(x), c_i64(x.shape[0]), _ptr(out)))
+        return out
+
+    def fp64_peak(self):
+        a, b = c_dbl(), c_dbl()
+        self._ck(self._lib.sdpcs_fp64_peak(self._ctx, ctypes.byref(a), ctypes.byref(b)))
+        return dict(dfma_tflops=a.value, dmma_tflops=b.value)
+
+
+def unrank(n, rho, ranks):
+    lib = load_library()
+    ranks = np.ascontiguousarray(ranks, dtype=np.int64).ravel()
+    out = np.empty((ranks.size, rho), dtype=np.int32)
+    rc = lib.sdpcs_unrank(c_int(n), c_int(rho), _ptr(ranks), c_i64(ranks.size), _ptr(out))
+    if rc != 0:
+        raise SdpcsError("sdpcs_unrank failed (%d)" % rc)
+    return out
+
+
+def binom(n, k):
+    lib = load_library()
+    out = c_i64()
+    if lib.sdpcs_binom(c_int(n), c_int(k), ctypes.byref(out)) != 0:
+        raise SdpcsError("sdpcs_binom: bad arguments")
+    return out.value

@@ -1,0 +1,939 @@
+// libsdpcutsel: C ABI (include/sdpcutsel.h) over the sm_100a kernels. Host logic only: buffers, launches,
+// pass sequencing. No CPU compute path exists -- every score, selection and cut is produced by a kernel.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sdpcutsel.h"
+#include "aux_kernels.cuh"
+#include "score_kernels.cuh"
+#include "select_kernels.cuh"
+
+using namespace sdpcs;
+
+static std::string g_create_error;
+
+struct sdpcs_ctx {
+    int device = 0;
+    int sms = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+    sdpcs_params params;
+    // instance
+    int n = 0;
+    double* d_Q = nullptr;
+    double* d_vars = nullptr;      // [X | x]
+    double* h_vars = nullptr;      // pinned staging
+    // weights (fragment-ordered), index = rho
+    double* d_wfrag[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // cover
+    int rho = 0, mode = 0;         // mode 0 none, 1 all-subsets, 2 list
+    i64 N = 0, base = 0;           // base = agg_idx of local candidate 0 (rank_begin / agg_offset)
+    uint8_t* d_idx[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    i64* d_pos[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    i64 Nd[6] = {0, 0, 0, 0, 0, 0};
+    // scores
+    double *d_lam = nullptr, *d_obj = nullptr;
+    i64 score_cap = 0;
+    int have = 0;
+    // selection scratch
+    u64 *d_key1 = nullptr, *d_key2 = nullptr;
+    i64 key_cap = 0, key2_cap = 0;
+    SelState* d_state = nullptr;
+    u64 *d_c_k1 = nullptr, *d_c_k2 = nullptr, *d_s_k1 = nullptr, *d_s_k2 = nullptr;
+    i64 *d_c_idx = nullptr, *d_s_idx = nullptr, *d_s_perm = nullptr;
+    double *d_o_score = nullptr, *d_o_lam = nullptr, *d_o_obj = nullptr;
+    i64 out_cap = 0;
+    void* h_out = nullptr;         // pinned download staging
+    size_t h_out_bytes = 0;
+    i64 last_counts[3] = {0, 0, 0};
+    // triangles
+    uint8_t* d_adj = nullptr;
+    bool have_adj = false;
+    unsigned long long* d_tri_counters = nullptr;
+    // generic scratch
+    void* d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    // timing
+    cudaEvent_t ev[6];
+    bool ev_score = false, ev_select = false, ev_h2d = false;
+    sdpcs_timings tm;
+
+    int fail(int code, const std::string& m) { err = m; return code; }
+};
+
+#define CU(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return ctx->fail(SDPCS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));      \
+    } while (0)
+
+template <typename T>
+static int ensure_dev(sdpcs_ctx* ctx, T*& p, i64& cap, i64 want)
+{
+    if (want <= cap && p) return SDPCS_OK;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    if ((size_t)want * sizeof(T) > free_b)
+        return ctx->fail(SDPCS_ERR_NOMEM, "shard needs " + std::to_string((size_t)want * sizeof(T)) +
+                                              " bytes, only " + std::to_string(free_b) + " free on device");
+    CU(cudaMalloc(&p, std::max<i64>(want, 1) * sizeof(T)));
+    cap = want;
+    return SDPCS_OK;
+}
+
+static int ensure_scratch(sdpcs_ctx* ctx, size_t bytes)
+{
+    if (bytes <= ctx->scratch_bytes) return SDPCS_OK;
+    if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    ctx->d_scratch = nullptr; ctx->scratch_bytes = 0;
+    CU(cudaMalloc(&ctx->d_scratch, bytes));
+    ctx->scratch_bytes = bytes;
+    return SDPCS_OK;
+}
+
+static int ensure_hout(sdpcs_ctx* ctx, size_t bytes)
+{
+    if (bytes <= ctx->h_out_bytes) return SDPCS_OK;
+    if (ctx->h_out) cudaFreeHost(ctx->h_out);
+    ctx->h_out = nullptr; ctx->h_out_bytes = 0;
+    CU(cudaMallocHost(&ctx->h_out, bytes));
+    ctx->h_out_bytes = bytes;
+    return SDPCS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// NN weights: blob -> DMMA fragment order (see mlp16 in score_kernels.cuh)
+// ---------------------------------------------------------------------------------------------------
+template <int D>
+static bool pack_fragments(const double* blob, i64 len, std::vector<double>& out, std::string& err)
+{
+    using C = NetCfg<D>;
+    if (len < 3) { err = "weight blob too short"; return false; }
+    const int n_in = (int)blob[0], L = (int)blob[1], h = (int)blob[2];
+    const i64 expect = 3 + 2 * n_in + (i64)h * n_in + h + (i64)(L - 2) * (h * h + h) + h + 1 + 2;
+    if (n_in != C::NIN || h != C::H || L != C::NHID + 1 || len != expect) {
+        err = "weight blob does not describe NN_" + std::to_string(D) + "D (n_in=" + std::to_string(n_in) +
+              " L=" + std::to_string(L) + " h=" + std::to_string(h) + " len=" + std::to_string(len) + ")";
+        return false;
+    }
+    const double* xo = blob + 3;
+    const double* xg = xo + n_in;
+    const double* p = xg + n_in;
+    std::vector<const double*> W(L), B(L);
+    for (int l = 0; l < L; ++l) {
+        int rows = (l == L - 1) ? 1 : h, cols = (l == 0) ? n_in : h;
+        W[l] = p; p += (i64)rows * cols;
+        B[l] = p; p += rows;
+    }
+    const double y_gain = p[0], y_xoff = p[1];
+    const double s = SDPCS_TANSIG_SCALE;
+    out.assign(C::BLOB, 0.0);
+    for (int ks = 0; ks < C::KS0; ++ks)
+        for (int nt = 0; nt < C::NT; ++nt)
+            for (int lane = 0; lane < 32; ++lane) {
+                int g = lane >> 2, t = lane & 3, nrn = 8 * nt + g, k = 4 * ks + t;
+                out[C::OFF_W0 + (ks * C::NT + nt) * 32 + lane] = (nrn < h && k < n_in) ? s * W[0][nrn * n_in + k] : 0.0;
+            }
+    for (int l = 1; l < C::NHID; ++l)
+        for (int kt = 0; kt < C::NT; ++kt)
+            for (int hh = 0; hh < 2; ++hh)
+                for (int nt = 0; nt < C::NT; ++nt)
+                    for (int lane = 0; lane < 32; ++lane) {
+                        int g = lane >> 2, t = lane & 3, nrn = 8 * nt + g, k = 8 * kt + 2 * t + hh, ks = 2 * kt + hh;
+                        out[C::OFF_WH + (l - 1) * (2 * C::NT * C::NT * 32) + (ks * C::NT + nt) * 32 + lane] =
+                            (nrn < h && k < h) ? s * W[l][nrn * h + k] : 0.0;
+                    }
+    for (int l = 0; l < C::NHID; ++l)
+        for (int j = 0; j < h; ++j) out[C::OFF_BIAS + l * C::HP + j] = s * B[l][j];
+    for (int j = 0; j < h; ++j) out[C::OFF_WOUT + j] = W[L - 1][j];
+    for (int j = 0; j < n_in; ++j) { out[C::OFF_XOFF + j] = xo[j]; out[C::OFF_GAIN + j] = xg[j]; }
+    out[C::OFF_MISC + 0] = B[L - 1][0];
+    out[C::OFF_MISC + 1] = y_gain;
+    out[C::OFF_MISC + 2] = y_xoff;
+    for (int j = 0; j < 256; ++j) out[C::OFF_TAB + j] = (double)exp2l((long double)j / 256.0L);
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// basic API
+// ---------------------------------------------------------------------------------------------------
+extern "C" int sdpcs_default_params(sdpcs_params* p)
+{
+    if (!p) return SDPCS_ERR_INVALID;
+    p->thres_min_opt = 0.0;
+    p->thres_neg_eigval = -1e-15;
+    p->big_m = 1000.0;
+    p->thres_tri_viol = 1e-7;
+    p->thres_tri_dense = 2;
+    p->jacobi_sweeps = 0;
+    return SDPCS_OK;
+}
+
+extern "C" const char* sdpcs_last_error(const sdpcs_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int sdpcs_create(sdpcs_ctx** out, int device)
+{
+    if (!out) return SDPCS_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (there is no CPU fallback)";
+        return SDPCS_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) { g_create_error = "bad device ordinal"; return SDPCS_ERR_INVALID; }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return SDPCS_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return SDPCS_ERR_CUDA; }
+    if (prop.major != 10) {
+        g_create_error = "libsdpcutsel is built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor);
+        return SDPCS_ERR_CUDA;
+    }
+    sdpcs_ctx* ctx = new sdpcs_ctx();
+    ctx->device = device;
+    ctx->sms = prop.multiProcessorCount;
+    sdpcs_default_params(&ctx->params);
+    memset(&ctx->tm, 0, sizeof(ctx->tm));
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&ctx->d_state, sizeof(SelState)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_tri_counters, 2 * sizeof(unsigned long long)) != cudaSuccess) {
+        g_create_error = "context allocation failed";
+        delete ctx;
+        return SDPCS_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    *out = ctx;
+    return SDPCS_OK;
+}
+
+extern "C" int sdpcs_destroy(sdpcs_ctx* ctx)
+{
+    if (!ctx) return SDPCS_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    void* ptrs[] = {ctx->d_Q, ctx->d_vars, ctx->d_lam, ctx->d_obj, ctx->d_key1, ctx->d_key2, ctx->d_state, ctx->d_c_k1,
+                    ctx->d_c_k2, ctx->d_s_k1, ctx->d_s_k2, ctx->d_c_idx, ctx->d_s_idx, ctx->d_s_perm, ctx->d_o_score,
+                    ctx->d_o_lam, ctx->d_o_obj, ctx->d_adj, ctx->d_tri_counters, ctx->d_scratch};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (int d = 0; d < 6; ++d) {
+        if (ctx->d_wfrag[d]) cudaFree(ctx->d_wfrag[d]);
+        if (ctx->d_idx[d]) cudaFree(ctx->d_idx[d]);
+        if (ctx->d_pos[d]) cudaFree(ctx->d_pos[d]);
+    }
+    if (ctx->h_vars) cudaFreeHost(ctx->h_vars);
+    if (ctx->h_out) cudaFreeHost(ctx->h_out);
+    for (auto& ev : ctx->ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return SDPCS_OK;
+}
+
+extern "C" int sdpcs_set_stream(sdpcs_ctx* ctx, void* s)
+{
+    if (!ctx) return SDPCS_ERR_INVALID;
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return SDPCS_OK;
+}
+
+extern "C" int sdpcs_set_params(sdpcs_ctx* ctx, const sdpcs_params* p)
+{
+    if (!ctx || !p) return SDPCS_ERR_INVALID;
+    ctx->params = *p;
+    return SDPCS_OK;
+}
+
+extern "C" int sdpcs_get_timings(const sdpcs_ctx* cctx, sdpcs_timings* t)
+{
+    sdpcs_ctx* ctx = const_cast<sdpcs_ctx*>(cctx);
+    if (!ctx || !t) return SDPCS_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float ms;
+    if (ctx->ev_h2d) { CU(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5])); ctx->tm.h2d_ms = ms; }
+    if (ctx->ev_score) { CU(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1])); ctx->tm.score_ms = ms; }
+    if (ctx->ev_select) { CU(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3])); ctx->tm.select_ms = ms; }
+    *t = ctx->tm;
+    return SDPCS_OK;
+}
+
+extern "C" int sdpcs_set_weights(sdpcs_ctx* ctx, int rho, const double* blob, int64_t len)
+{
+    if (!ctx || !blob || rho < 2 || rho > 5) return ctx ? ctx->fail(SDPCS_ERR_INVALID, "rho must be 2..5") : SDPCS_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    std::vector<double> frag;
+    std::string err;
+    bool ok = false;
+    switch (rho) {
+    case 2: ok = pack_fragments<2>(blob, len, frag, err); break;
+    case 3: ok = pack_fragments<3>(blob, len, frag, err); break;
+    case 4: ok = pack_fragments<4>(blob, len, frag, err); break;
+    case 5: ok = pack_fragments<5>(blob, len, frag, err); break;
+    }
+    if (!ok) return ctx->fail(SDPCS_ERR_INVALID, err);
+    if (ctx->d_wfrag[rho]) { cudaFree(ctx->d_wfrag[rho]); ctx->d_wfrag[rho] = nullptr; }
+    CU(cudaMalloc(&ctx->d_wfrag[rho], frag.size() * sizeof(double)));
+    CU(cudaMemcpyAsync(ctx->d_wfrag[rho], frag.data(), frag.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SDPCS_OK;
+}
+
+extern "C" int sdpcs_set_instance(sdpcs_ctx* ctx, int n, const double* Q_arr)
+{
+    if (!ctx || !Q_arr || n < 2 || n > SDPCS_MAX_N) return ctx ? ctx->fail(SDPCS_ERR_INVALID, "need 2 <= n <= 250") : SDPCS_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const size_t nl = (size_t)n * (n + 1) / 2;
+    if (ctx->d_Q) cudaFree(ctx->d_Q);
+    if (ctx->d_vars) cudaFree(ctx->d_vars);
+    if (ctx->h_vars) cudaFreeHost(ctx->h_vars);
+    ctx->d_Q = ctx->d_vars = ctx->h_vars = nullptr;
+    CU(cudaMalloc(&ctx->d_Q, nl * sizeof(double)));
+    CU(cudaMalloc(&ctx->d_vars, (nl + n) * sizeof(double)));
+    CU(cudaMallocHost(&ctx->h_vars, (nl + n) * sizeof(double)));
+    CU(cudaMemcpyAsync(ctx->d_Q, Q_arr, nl * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->n = n;
+    ctx->mode = 0; ctx->N = 0; ctx->have = 0;
+    ctx->have_adj = false;
+    return SDPCS_OK;
+}
+
+extern "C" int sdpcs_binom(int n, int k, int64_t* out)
+{
+    if (!out || n < 0 || n > SDPCS_MAX_N || k < 0 || k > SDPCS_MAX_RHO) return SDPCS_ERR_INVALID;
+    *out = (int64_t)binom_small(n, k);
+    return SDPCS_OK;
+}
+
+extern "C" int sdpcs_unrank(int n, int rho, const int64_t* ranks, int64_t m, int32_t* out_idx)
+{
+    if (!ranks || !out_idx || n < rho || n > SDPCS_MAX_N || rho < 1 || rho > SDPCS_MAX_RHO || m < 0) return SDPCS_ERR_INVALID;
+    const i64 total = (i64)binom_small(n, rho);
+    for (i64 i = 0; i < m; ++i) {
+        if (ranks[i] < 0 || ranks[i] >= total) return SDPCS_ERR_INVALID;
+        int c[5];
+        switch (rho) {
+        case 1: out_idx[i] = (int32_t)ranks[i]; continue;
+        case 2: { int cc[2]; lex_unrank<2>(n, (u64)ranks[i], cc); c[0] = cc[0]; c[1] = cc[1]; } break;
+        case 3: { int cc[3]; lex_unrank<3>(n, (u64)ranks[i], cc); for (int t = 0; t < 3; ++t) c[t] = cc[t]; } break;
+        case 4: { int cc[4]; lex_unrank<4>(n, (u64)ranks[i], cc); for (int t = 0; t < 4; ++t) c[t] = cc[t]; } break;
+        default: { int cc[5]; lex_unrank<5>(n, (u64)ranks[i], cc); for (int t = 0; t < 5; ++t) c[t] = cc[t]; } break;
+        }
+        for (int t = 0; t < rho; ++t) out_idx[i * rho + t] = c[t];
+    }
+    return SDPCS_OK;
+}
+
+static int alloc_scores(sdpcs_ctx* ctx, i64 N)
+{
+    i64 cap2 = ctx->score_cap;
+    int rc = ensure_dev(ctx, ctx->d_lam, ctx->score_cap, N);
+    if (rc) return rc;
+    rc = ensure_dev(ctx, ctx->d_obj, cap2, N);
+    if (rc) return rc;
+    return SDPCS_OK;
+}
+
+extern "C" int sdpcs_set_cover_all(sdpcs_ctx* ctx, int rho, int64_t rank_begin, int64_t rank_end)
+{
+    if (!ctx) return SDPCS_ERR_INVALID;
+    if (!ctx->n) return ctx->fail(SDPCS_ERR_STATE, "set_instance first");
+    if (rho < 2 || rho > 5 || rho > ctx->n) return ctx->fail(SDPCS_ERR_INVALID, "rho must be 2..5");
+    CU(cudaSetDevice(ctx->device));
+    const i64 total = (i64)binom_small(ctx->n, rho);
+    if (rank_end < 0) rank_end = total;
+    if (rank_begin < 0 || rank_begin > rank_end || rank_end > total) return ctx->fail(SDPCS_ERR_INVALID, "bad rank range");
+    ctx->mode = 0; ctx->have = 0;
+    // both score arrays must fit
+    if (ctx->d_lam && ctx->score_cap < rank_end - rank_begin) { cudaFree(ctx->d_lam); cudaFree(ctx->d_obj); ctx->d_lam = ctx->d_obj = nullptr; ctx->score_cap = 0; }
+    int rc = alloc_scores(ctx, rank_end - rank_begin);
+    if (rc) return rc;
+    ctx->rho = rho; ctx->mode = 1; ctx->base = rank_begin; ctx->N = rank_end - rank_begin;
+    return SDPCS_OK;
+}
+
+extern "C" int sdpcs_set_cover_list(sdpcs_ctx* ctx, int rho, const int16_t* idx, int64_t N, int64_t agg_offset)
+{
+    if (!ctx) return SDPCS_ERR_INVALID;
+    if (!ctx->n) return ctx->fail(SDPCS_ERR_STATE, "set_instance first");
+    if (rho < 2 || rho > 5 || N < 0 || (N > 0 && !idx)) return ctx->fail(SDPCS_ERR_INVALID, "bad cover list");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->mode = 0; ctx->have = 0;
+    std::vector<uint8_t> packed[6];
+    std::vector<i64> pos[6];
+    for (i64 i = 0; i < N; ++i) {
+        const int16_t* r = idx + i * rho;
+        int d = 0;
+        while (d < rho && r[d] >= 0) ++d;
+        for (int t = d; t < rho; ++t) if (r[t] >= 0) return ctx->fail(SDPCS_ERR_INVALID, "cover row " + std::to_string(i) + ": -1 padding must trail");
+        if (d < 2) return ctx->fail(SDPCS_ERR_INVALID, "cover row " + std::to_string(i) + " has fewer than 2 indices");
+        for (int t = 0; t < d; ++t) {
+            if (r[t] >= ctx->n || (t && r[t] <= r[t - 1])) return ctx->fail(SDPCS_ERR_INVALID, "cover row " + std::to_string(i) + " not strictly ascending in [0,n)");
+            packed[d].push_back((uint8_t)r[t]);
+        }
+        pos[d].push_back(i);
+    }
+    for (int d = 2; d <= 5; ++d) {
+        if (ctx->d_idx[d]) { cudaFree(ctx->d_idx[d]); ctx->d_idx[d] = nullptr; }
+        if (ctx->d_pos[d]) { cudaFree(ctx->d_pos[d]); ctx->d_pos[d] = nullptr; }
+        ctx->Nd[d] = (i64)pos[d].size();
+        if (!ctx->Nd[d]) continue;
+        CU(cudaMalloc(&ctx->d_idx[d], packed[d].size()));
+        CU(cudaMalloc(&ctx->d_pos[d], pos[d].size() * sizeof(i64)));
+        CU(cudaMemcpy(ctx->d_idx[d], packed[d].data(), packed[d].size(), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(ctx->d_pos[d], pos[d].data(), pos[d].size() * sizeof(i64), cudaMemcpyHostToDevice));
+    }
+    if (ctx->d_lam && ctx->score_cap < N) { cudaFree(ctx->d_lam); cudaFree(ctx->d_obj); ctx->d_lam = ctx->d_obj = nullptr; ctx->score_cap = 0; }
+    int rc = alloc_scores(ctx, N);
+    if (rc) return rc;
+    ctx->rho = rho; ctx->mode = 2; ctx->base = agg_offset; ctx->N = N;
+    return SDPCS_OK;
+}
+
+extern "C" int sdpcs_num_candidates(const sdpcs_ctx* ctx, int64_t* N)
+{
+    if (!ctx || !N) return SDPCS_ERR_INVALID;
+    *N = ctx->N;
+    return SDPCS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// scoring
+// ---------------------------------------------------------------------------------------------------
+static int upload_vars(sdpcs_ctx* ctx, const double* vars_values)
+{
+    const size_t len = (size_t)ctx->n * (ctx->n + 1) / 2 + ctx->n;
+    CU(cudaStreamSynchronize(ctx->stream));   // pinned staging buffer is reused
+    memcpy(ctx->h_vars, vars_values, len * sizeof(double));
+    CU(cudaEventRecord(ctx->ev[4], ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_vars, ctx->h_vars, len * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaEventRecord(ctx->ev[5], ctx->stream));
+    ctx->ev_h2d = true;
+    return SDPCS_OK;
+}
+
+constexpr int FULL_WARPS = 8;
+
+template <int D>
+static int launch_score(sdpcs_ctx* ctx, int want, const uint8_t* idx, const i64* pos, i64 N, i64 rank_begin)
+{
+    if (N <= 0) return SDPCS_OK;
+    ScoreArgs a;
+    a.n = ctx->n; a.N = N; a.rank_begin = rank_begin; a.idx = idx; a.pos = pos;
+    a.X = ctx->d_vars; a.x = ctx->d_vars + (size_t)ctx->n * (ctx->n + 1) / 2; a.Q = ctx->d_Q;
+    a.wfrag = ctx->d_wfrag[D]; a.lam = ctx->d_lam; a.obj = ctx->d_obj;
+    a.sweeps = ctx->params.jacobi_sweeps > 0 ? ctx->params.jacobi_sweeps : default_sweeps(D + 1);
+    const i64 groups = (N + 31) / 32;
+    if (!(want & 2)) {
+        int occ = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_score_feas<D>, 256, 0));
+        i64 grid = std::min<i64>((groups + 7) / 8, (i64)ctx->sms * std::max(occ, 1));
+        k_score_feas<D><<<(unsigned)std::max<i64>(grid, 1), 256, 0, ctx->stream>>>(a);
+    } else {
+        if (!a.wfrag) return ctx->fail(SDPCS_ERR_STATE, "NN_" + std::to_string(D) + "D weights not set");
+        const size_t smem = (size_t)score_full_smem_doubles<D>(FULL_WARPS) * sizeof(double);
+        int occ = 0;
+        if (want & 1) {
+            auto kern = k_score_full<D, true, FULL_WARPS>;
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, FULL_WARPS * 32, smem));
+            i64 grid = std::min<i64>((groups + FULL_WARPS - 1) / FULL_WARPS, (i64)ctx->sms * std::max(occ, 1));
+            kern<<<(unsigned)std::max<i64>(grid, 1), FULL_WARPS * 32, smem, ctx->stream>>>(a);
+        } else {
+            auto kern = k_score_full<D, false, FULL_WARPS>;
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, FULL_WARPS * 32, smem));
+            i64 grid = std::min<i64>((groups + FULL_WARPS - 1) / FULL_WARPS, (i64)ctx->sms * std::max(occ, 1));
+            kern<<<(unsigned)std::max<i64>(grid, 1), FULL_WARPS * 32, smem, ctx->stream>>>(a);
+        }
+    }
+    CU(cudaGetLastError());
+    ctx->tm.score_launches++;
+    return SDPCS_OK;
+}
+
+static int launch_score_d(sdpcs_ctx* ctx, int d, int want, const uint8_t* idx, const i64* pos, i64 N, i64 rb)
+{
+    switch (d) {
+    case 2: return launch_score<2>(ctx, want, idx, pos, N, rb);
+    case 3: return launch_score<3>(ctx, want, idx, pos, N, rb);
+    case 4: return launch_score<4>(ctx, want, idx, pos, N, rb);
+    case 5: return launch_score<5>(ctx, want, idx, pos, N, rb);
+    }
+    return ctx->fail(SDPCS_ERR_INVALID, "bad subset size");
+}
+
+static int score_device(sdpcs_ctx* ctx, int want)
+{
+    if (!ctx->mode) return ctx->fail(SDPCS_ERR_STATE, "cover not set");
+    if (!(want & 3)) return ctx->fail(SDPCS_ERR_INVALID, "want must have bit 0 (lam) and/or bit 1 (obj)");
+    ctx->tm.score_launches = 0;
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    int rc = SDPCS_OK;
+    if (ctx->mode == 1) rc = launch_score_d(ctx, ctx->rho, want, nullptr, nullptr, ctx->N, ctx->base);
+    else
+        for (int d = 2; d <= ctx->rho && rc == SDPCS_OK; ++d)
+            rc = launch_score_d(ctx, d, want, ctx->d_idx[d], ctx->d_pos[d], ctx->Nd[d], 0);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    ctx->ev_score = true;
+    ctx->have = want & 3;
+    return SDPCS_OK;
+}
+
+extern "C" int sdpcs_score(sdpcs_ctx* ctx, const double* vars_values, int want)
+{
+    if (!ctx || !vars_values) return SDPCS_ERR_INVALID;
+    if (!ctx->mode) return ctx->fail(SDPCS_ERR_STATE, "cover not set");
+    CU(cudaSetDevice(ctx->device));
+    int rc = upload_vars(ctx, vars_values);
+    if (rc) return rc;
+    return score_device(ctx, want);
+}
+
+extern "C" int sdpcs_scores(sdpcs_ctx* ctx, int64_t i0, int64_t i1, double* out_lam, double* out_obj)
+{
+    if (!ctx) return SDPCS_ERR_INVALID;
+    if (i0 < 0 || i1 < i0 || i1 > ctx->N) return ctx->fail(SDPCS_ERR_INVALID, "bad range");
+    if ((out_lam && !(ctx->have & 1)) || (out_obj && !(ctx->have & 2))) return ctx->fail(SDPCS_ERR_STATE, "requested scores not resident");
+    CU(cudaSetDevice(ctx->device));
+    if (out_lam) CU(cudaMemcpyAsync(out_lam, ctx->d_lam + i0, (i1 - i0) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_obj) CU(cudaMemcpyAsync(out_obj, ctx->d_obj + i0, (i1 - i0) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SDPCS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// selection
+// ---------------------------------------------------------------------------------------------------
+static int ensure_out(sdpcs_ctx* ctx, i64 k)
+{
+    if (k <= ctx->out_cap) return SDPCS_OK;
+    void** ptrs[] = {(void**)&ctx->d_c_k1, (void**)&ctx->d_c_k2, (void**)&ctx->d_s_k1, (void**)&ctx->d_s_k2, (void**)&ctx->d_c_idx,
+                     (void**)&ctx->d_s_idx, (void**)&ctx->d_s_perm, (void**)&ctx->d_o_score, (void**)&ctx->d_o_lam, (void**)&ctx->d_o_obj};
+    for (void** p : ptrs) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+        CU(cudaMalloc(p, (size_t)k * 8));
+    }
+    ctx->out_cap = k;
+    return SDPCS_OK;
+}
+
+// radix-select + collect + sort over (key1, key2, idx); results in d_s_k1/d_s_k2/d_s_idx, count in state
+static int run_select(sdpcs_ctx* ctx, const u64* key1, const u64* key2, const i64* idx, i64 N, i64 base, i64 k)
+{
+    SelArgs sa{key1, key2, idx, N, base, ctx->d_state};
+    const int threads = 512;
+    const unsigned grid = (unsigned)std::max<i64>(1, std::min<i64>((N + threads - 1) / threads, (i64)ctx->sms * 4));
+    static const int shifts0[6] = {53, 42, 31, 20, 10, 0}, widths0[6] = {11, 11, 11, 11, 10, 10};
+    for (int p = 0; p < 6; ++p) {
+        k_sel_hist<<<grid, threads, 0, ctx->stream>>>(sa, 0, shifts0[p], widths0[p], p == 0);
+        k_sel_scan<<<1, 1024, 0, ctx->stream>>>(ctx->d_state, 0, shifts0[p], widths0[p], p == 0, p == 5, key2 ? 1 : 2, k);
+    }
+    if (key2)
+        for (int p = 0; p < 6; ++p) {
+            k_sel_hist<<<grid, threads, 0, ctx->stream>>>(sa, 1, shifts0[p], widths0[p], 0);
+            k_sel_scan<<<1, 1024, 0, ctx->stream>>>(ctx->d_state, 1, shifts0[p], widths0[p], 0, p == 5, 2, k);
+        }
+    for (int p = 0; p < 4; ++p) {
+        k_sel_hist<<<grid, threads, 0, ctx->stream>>>(sa, 2, 33 - 11 * p, 11, 0);
+        k_sel_scan<<<1, 1024, 0, ctx->stream>>>(ctx->d_state, 2, 33 - 11 * p, 11, 0, p == 3, -1, k);
+    }
+    const unsigned cgrid = (unsigned)std::max<i64>(1, std::min<i64>((N + 255) / 256, (i64)ctx->sms * 8));
+    k_sel_collect<<<cgrid, 256, 0, ctx->stream>>>(sa, ctx->out_cap, ctx->d_c_k1, ctx->d_c_k2, ctx->d_c_idx);
+    k_rank_sort<<<(unsigned)((k + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_state, 0, ctx->d_c_k1, ctx->d_c_k2, ctx->d_c_idx,
+                                                                        ctx->d_s_k1, ctx->d_s_k2, ctx->d_s_idx);
+    CU(cudaGetLastError());
+    ctx->tm.select_launches += 2 * (6 + (key2 ? 6 : 0) + 4) + 2;
+    return SDPCS_OK;
+}
+
+static int topk_device(sdpcs_ctx* ctx, int mode, i64 k, double pivot_obj, i64 pivot_idx, int all_walked)
+{
+    if (mode < 1 || mode > 4) return ctx->fail(SDPCS_ERR_INVALID, "mode must be 1..4");
+    const int need = (mode == 1) ? 1 : (mode == 2) ? 2 : 3;
+    if ((ctx->have & need) != need) return ctx->fail(SDPCS_ERR_STATE, "scores needed by this mode are not resident; call sdpcs_score");
+    if (k < 0) return ctx->fail(SDPCS_ERR_INVALID, "k < 0");
+    k = std::min<i64>(k, ctx->N);
+    int rc = ensure_dev(ctx, ctx->d_key1, ctx->key_cap, ctx->N);
+    if (rc) return rc;
+    if (mode == 4 && (rc = ensure_dev(ctx, ctx->d_key2, ctx->key2_cap, ctx->N))) return rc;
+    if ((rc = ensure_out(ctx, std::max<i64>(k, 1)))) return rc;
+    CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+    ctx->tm.select_launches = 0;
+    k_sel_reset<<<1, 256, 0, ctx->stream>>>(ctx->d_state);
+    KeyArgs ka;
+    ka.lam = (ctx->have & 1) ? ctx->d_lam : nullptr;
+    ka.obj = (ctx->have & 2) ? ctx->d_obj : nullptr;
+    ka.N = ctx->N; ka.base = ctx->base; ka.mode = mode;
+    ka.thr_eig = ctx->params.thres_neg_eigval; ka.thr_opt = ctx->params.thres_min_opt; ka.big_m = ctx->params.big_m;
+    ka.pivot_obj = pivot_obj; ka.pivot_idx = pivot_idx; ka.all_walked = all_walked;
+    ka.key1 = ctx->d_key1; ka.key2 = (mode == 4) ? ctx->d_key2 : nullptr; ka.st = ctx->d_state;
+    const unsigned grid = (unsigned)std::max<i64>(1, std::min<i64>((ctx->N + 255) / 256, (i64)ctx->sms * 8));
+    k_make_keys<<<grid, 256, 0, ctx->stream>>>(ka);
+    ctx->tm.select_launches += 2;
+    if (k > 0) {
+        rc = run_select(ctx, ctx->d_key1, ka.key2, nullptr, ctx->N, ctx->base, k);
+        if (rc) return rc;
+        k_sel_gather<<<(unsigned)std::max<i64>(1, (k + 255) / 256), 256, 0, ctx->stream>>>(
+            ctx->d_state, ctx->d_s_k1, ctx->d_s_idx, ctx->base, ka.lam, ka.obj, ctx->d_o_score, ctx->d_o_lam, ctx->d_o_obj);
+        ctx->tm.select_launches++;
+    }
+    CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+    ctx->ev_select = true;
+    CU(cudaGetLastError());
+    return SDPCS_OK;
+}
+
+// download state + the k winners
+static int download_topk(sdpcs_ctx* ctx, i64 k, int64_t* out_idx, double* out_score, double* out_lam, double* out_obj, int64_t* out_n)
+{
+    k = std::min<i64>(k, ctx->N);
+    const size_t kb = (size_t)std::max<i64>(k, 1) * 8;
+    int rc = ensure_hout(ctx, sizeof(SelState) + 4 * kb);
+    if (rc) return rc;
+    char* h = (char*)ctx->h_out;
+    CU(cudaMemcpyAsync(h, ctx->d_state, sizeof(SelState), cudaMemcpyDeviceToHost, ctx->stream));
+    if (k > 0) {
+        CU(cudaMemcpyAsync(h + sizeof(SelState), ctx->d_s_idx, k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(h + sizeof(SelState) + kb, ctx->d_o_score, k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(h + sizeof(SelState) + 2 * kb, ctx->d_o_lam, k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(h + sizeof(SelState) + 3 * kb, ctx->d_o_obj, k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    const SelState* st = (const SelState*)h;
+    i64 m = k > 0 ? std::min<i64>((i64)st->out_count, k) : 0;
+    ctx->last_counts[0] = ctx->N; ctx->last_counts[1] = st->n_violated; ctx->last_counts[2] = st->n_strong;
+    if (out_n) *out_n = m;
+    if (out_idx) memcpy(out_idx, h + sizeof(SelState), m * 8);
+    if (out_score) memcpy(out_score, h + sizeof(SelState) + kb, m * 8);
+    if (out_lam) memcpy(out_lam, h + sizeof(SelState) + 2 * kb, m * 8);
+    if (out_obj) memcpy(out_obj, h + sizeof(SelState) + 3 * kb, m * 8);
+    return SDPCS_OK;
+}
+
+extern "C" int sdpcs_topk(sdpcs_ctx* ctx, int mode, int64_t k, double pivot_obj, int64_t pivot_idx, int all_walked,
+                          int64_t* out_idx, double* out_score, double* out_lam, double* out_obj, int64_t* out_n)
+{
+    if (!ctx) return SDPCS_ERR_INVALID;
+    if (!ctx->mode) return ctx->fail(SDPCS_ERR_STATE, "cover not set");
+    CU(cudaSetDevice(ctx->device));
+    int rc = topk_device(ctx, mode, k, pivot_obj, pivot_idx, all_walked);
+    if (rc) return rc;
+    return download_topk(ctx, k, out_idx, out_score, out_lam, out_obj, out_n);
+}
+
+extern "C" int sdpcs_counts(sdpcs_ctx* ctx, int64_t* out3)
+{
+    if (!ctx || !out3) return SDPCS_ERR_INVALID;
+    out3[0] = ctx->last_counts[0]; out3[1] = ctx->last_counts[1]; out3[2] = ctx->last_counts[2];
+    return SDPCS_OK;
+}
+
+extern "C" int sdpcs_select(sdpcs_ctx* ctx, int strat, const double* vars_values, int64_t k, int64_t* out_idx,
+                            double* out_score, double* out_lam, double* out_obj, int64_t* out_n, int64_t* out_counts,
+                            int* out_new_strat)
+{
+    if (!ctx || !vars_values) return SDPCS_ERR_INVALID;
+    if (strat != 1 && strat != 2 && strat != 4) return ctx->fail(SDPCS_ERR_INVALID, "strat must be 1, 2 or 4");
+    if (!ctx->mode) return ctx->fail(SDPCS_ERR_STATE, "cover not set");
+    CU(cudaSetDevice(ctx->device));
+    k = std::min<i64>(std::max<i64>(k, 0), ctx->N);       // sel_size = min(sel_size, len(agg_list)), cut_select_qp.py:550
+    int rc = upload_vars(ctx, vars_values);
+    if (rc) return rc;
+    if ((rc = score_device(ctx, strat == 1 ? 1 : strat == 2 ? 2 : 3))) return rc;
+    int new_strat = strat;
+    i64 counts[3] = {ctx->N, 0, 0};
+    if (strat != 4) {
+        if ((rc = topk_device(ctx, strat, k, 0.0, 0, 0))) return rc;
+        if ((rc = download_topk(ctx, k, out_idx, out_score, out_lam, out_obj, out_n))) return rc;
+        counts[1] = ctx->last_counts[1];
+    } else {
+        // pass 1: the strong set S (obj > 0 and violated) by (obj desc, idx asc) -> pivot
+        std::vector<int64_t> sidx(std::max<i64>(k, 1));
+        std::vector<double> sobj(std::max<i64>(k, 1));
+        int64_t ns = 0;
+        if ((rc = topk_device(ctx, 3, k, 0.0, 0, 0))) return rc;
+        if ((rc = download_topk(ctx, k, sidx.data(), nullptr, nullptr, sobj.data(), &ns))) return rc;
+        const i64 n_viol = ctx->last_counts[1], n_strong_total = ctx->last_counts[2];
+        const bool all_walked = n_strong_total < k || k == 0;
+        const double pobj = all_walked ? 0.0 : sobj[k - 1];
+        const i64 pidx = all_walked ? 0 : sidx[k - 1];
+        float ms1 = 0;
+        cudaEventElapsedTime(&ms1, ctx->ev[2], ctx->ev[3]);
+        // pass 2: final measure of cut_select_qp.py:603-625
+        if ((rc = topk_device(ctx, 4, k, pobj, pidx, all_walked ? 1 : 0))) return rc;
+        if ((rc = download_topk(ctx, k, out_idx, out_score, out_lam, out_obj, out_n))) return rc;
+        float ms2 = 0;
+        cudaEventElapsedTime(&ms2, ctx->ev[2], ctx->ev[3]);
+        ctx->tm.select_ms = ms1 + ms2;
+        ctx->ev_select = false;
+        const i64 strong = std::min<i64>(n_strong_total, k);
+        const i64 viol_walked = all_walked ? n_viol : k;
+        counts[1] = viol_walked; counts[2] = strong;
+        if (k > 0 && ctx->N > 0)
+            new_strat = ((double)strong / (double)k < (double)viol_walked / (double)ctx->N) ? 1 : 4;   // cut_select_qp.py:629
+    }
+    if (out_counts) { out_counts[0] = counts[0]; out_counts[1] = counts[1]; out_counts[2] = counts[2]; }
+    if (out_new_strat) *out_new_strat = new_strat;
+    return SDPCS_OK;
+}
+
+extern "C" int sdpcs_merge_topk(sdpcs_ctx* ctx, int64_t m, const double* score, const double* obj2, const int64_t* idx,
+                                int64_t k, int64_t* out_perm, int64_t* out_n)
+{
+    if (!ctx || m < 0 || (m && (!score || !idx)) || !out_perm || !out_n) return SDPCS_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    *out_n = 0;
+    if (m == 0 || k <= 0) return SDPCS_OK;
+    // scratch: score, obj2, idx, k1, k2, sorted k1/k2/idx, perm  (9 arrays of m)
+    int rc = ensure_scratch(ctx, (size_t)m * 8 * 9);
+    if (rc) return rc;
+    double* d_score = (double*)ctx->d_scratch;
+    double* d_obj2 = d_score + m;
+    i64* d_idx = (i64*)(d_obj2 + m);
+    u64* d_k1 = (u64*)(d_idx + m);
+    u64* d_k2 = d_k1 + m;
+    u64* d_s1 = d_k2 + m;
+    u64* d_s2 = d_s1 + m;
+    i64* d_si = (i64*)(d_s2 + m);
+    i64* d_pp = d_si + m;
+    CU(cudaMemcpyAsync(d_score, score, m * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (obj2) CU(cudaMemcpyAsync(d_obj2, obj2, m * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_idx, idx, m * 8, cudaMemcpyHostToDevice, ctx->stream));
+    k_merge_keys<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(m, d_score, obj2 ? d_obj2 : nullptr, d_k1, d_k2);
+    // rank sort all m entries (m = shards * k is small); positions travel in the "idx" payload of a second sort key
+    // -> sort by (k1, k2, idx) and recover the permutation by sorting the position array alongside
+    k_rank_sort<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(nullptr, m, d_k1, d_k2, d_idx, d_s1, d_s2, d_si);
+    CU(cudaGetLastError());
+    std::vector<i64> sorted_idx(m), in_idx(idx, idx + m);
+    CU(cudaMemcpyAsync(sorted_idx.data(), d_si, m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    (void)d_pp;
+    // agg_idx values are unique across shards: map them back to input positions
+    std::vector<std::pair<i64, i64>> where(m);
+    for (i64 i = 0; i < m; ++i) where[i] = {in_idx[i], i};
+    std::sort(where.begin(), where.end());
+    const i64 take = std::min<i64>(k, m);
+    for (i64 i = 0; i < take; ++i) {
+        auto it = std::lower_bound(where.begin(), where.end(), std::make_pair(sorted_idx[i], (i64)-1));
+        out_perm[i] = it->second;
+    }
+    *out_n = take;
+    return SDPCS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// cuts, eigendecomposition, triangles, NN, peaks
+// ---------------------------------------------------------------------------------------------------
+extern "C" int sdpcs_gen_cuts(sdpcs_ctx* ctx, int rho, const int16_t* sets, int64_t m, const double* vars_values,
+                              int64_t* out_ind, double* out_val, double* out_rhs, double* out_lam, uint8_t* out_violated)
+{
+    if (!ctx || m < 0 || rho < 2 || rho > 5) return SDPCS_ERR_INVALID;
+    if (!ctx->n) return ctx->fail(SDPCS_ERR_STATE, "set_instance first");
+    if (m == 0) return SDPCS_OK;
+    if (!sets || !vars_values || !out_ind || !out_val || !out_rhs || !out_lam || !out_violated) return ctx->fail(SDPCS_ERR_INVALID, "null pointer");
+    for (i64 i = 0; i < m * rho; ++i)
+        if (sets[i] >= ctx->n) return ctx->fail(SDPCS_ERR_INVALID, "subset index out of range");
+    CU(cudaSetDevice(ctx->device));
+    int rc = upload_vars(ctx, vars_values);
+    if (rc) return rc;
+    const int width = rho + rho * (rho + 1) / 2;
+    const size_t b_sets = ((size_t)m * rho * 2 + 255) / 256 * 256, b_w = (size_t)m * width * 8, b_m = (size_t)m * 8;
+    if ((rc = ensure_scratch(ctx, b_sets + 2 * b_w + 3 * b_m))) return rc;
+    char* s = (char*)ctx->d_scratch;
+    CutArgs a;
+    a.n = ctx->n; a.rho = rho; a.m = m;
+    a.sets = (const int16_t*)s;
+    a.ind = (i64*)(s + b_sets); a.val = (double*)(s + b_sets + b_w);
+    a.rhs = (double*)(s + b_sets + 2 * b_w); a.lam = a.rhs + m; a.violated = (uint8_t*)(a.lam + m);
+    a.X = ctx->d_vars; a.x = ctx->d_vars + (size_t)ctx->n * (ctx->n + 1) / 2;
+    a.thr_eig = ctx->params.thres_neg_eigval;
+    a.sweeps = ctx->params.jacobi_sweeps > 0 ? ctx->params.jacobi_sweeps : default_sweeps(rho + 1);
+    CU(cudaMemcpyAsync(s, sets, (size_t)m * rho * 2, cudaMemcpyHostToDevice, ctx->stream));
+    k_gen_cuts<<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(a);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out_ind, a.ind, b_w, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(out_val, a.val, b_w, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(out_rhs, a.rhs, b_m, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(out_lam, a.lam, b_m, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(out_violated, a.violated, (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SDPCS_OK;
+}
+
+extern "C" int sdpcs_eigendecomp(sdpcs_ctx* ctx, int d, const double* curr_pt, const double* X_slice, double* out_vals,
+                                 double* out_vecs)
+{
+    if (!ctx || d < 2 || d > 5 || !curr_pt || !X_slice || !out_vals) return SDPCS_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    const int M = d + 1, t = d * (d + 1) / 2;
+    int rc = ensure_scratch(ctx, 8 * (size_t)(d + t + M + M * M));
+    if (rc) return rc;
+    double* s = (double*)ctx->d_scratch;
+    CU(cudaMemcpyAsync(s, curr_pt, d * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(s + d, X_slice, t * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const int sweeps = ctx->params.jacobi_sweeps > 0 ? ctx->params.jacobi_sweeps : default_sweeps(M);
+    k_eig_one<<<1, 1, 0, ctx->stream>>>(d, s, s + d, sweeps, s + d + t, s + d + t + M);
+    CU(cudaGetLastError());
+    double vals[6], vecs[36];
+    CU(cudaMemcpyAsync(vals, s + d + t, M * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(vecs, s + d + t + M, M * M * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    int order[6];
+    for (int i = 0; i < M; ++i) order[i] = i;
+    std::stable_sort(order, order + M, [&](int a, int b) { return vals[a] < vals[b]; });   // ascending, as LAPACK
+    for (int j = 0; j < M; ++j) {
+        out_vals[j] = vals[order[j]];
+        if (out_vecs)
+            for (int i = 0; i < M; ++i) out_vecs[i * M + j] = vecs[i * M + order[j]];
+    }
+    return SDPCS_OK;
+}
+
+extern "C" int sdpcs_set_tri_pattern(sdpcs_ctx* ctx, const uint8_t* adj)
+{
+    if (!ctx) return SDPCS_ERR_INVALID;
+    if (!ctx->n) return ctx->fail(SDPCS_ERR_STATE, "set_instance first");
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->d_adj) { cudaFree(ctx->d_adj); ctx->d_adj = nullptr; }
+    ctx->have_adj = false;
+    if (!adj) return SDPCS_OK;
+    CU(cudaMalloc(&ctx->d_adj, (size_t)ctx->n * ctx->n));
+    CU(cudaMemcpy(ctx->d_adj, adj, (size_t)ctx->n * ctx->n, cudaMemcpyHostToDevice));
+    ctx->have_adj = true;
+    return SDPCS_OK;
+}
+
+extern "C" int sdpcs_triangles(sdpcs_ctx* ctx, const double* vars_values, int64_t kmax, int64_t* out_triple_rank,
+                               int8_t* out_type, double* out_viol, int8_t* out_density, int64_t* out_n,
+                               int64_t* out_n_violated, int64_t* out_n_triples)
+{
+    if (!ctx || !vars_values || kmax < 0 || !out_n) return SDPCS_ERR_INVALID;
+    if (!ctx->n) return ctx->fail(SDPCS_ERR_STATE, "set_instance first");
+    if (ctx->n < 3) return ctx->fail(SDPCS_ERR_INVALID, "n < 3");
+    CU(cudaSetDevice(ctx->device));
+    int rc = upload_vars(ctx, vars_values);
+    if (rc) return rc;
+    const i64 T = (i64)binom_small(ctx->n, 3), NK = 4 * T;
+    kmax = std::min<i64>(kmax, NK);
+    if ((rc = ensure_dev(ctx, ctx->d_key1, ctx->key_cap, NK))) return rc;
+    if ((rc = ensure_out(ctx, std::max<i64>(kmax, 1)))) return rc;
+    CU(cudaMemsetAsync(ctx->d_tri_counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    TriArgs ta;
+    ta.n = ctx->n; ta.T = T; ta.X = ctx->d_vars; ta.x = ctx->d_vars + (size_t)ctx->n * (ctx->n + 1) / 2;
+    ta.adj = ctx->have_adj ? ctx->d_adj : nullptr;
+    ta.thres_dense = ctx->params.thres_tri_dense; ta.thres_viol = ctx->params.thres_tri_viol;
+    ta.key = ctx->d_key1; ta.counters = ctx->d_tri_counters;
+    const i64 groups = (T + 31) / 32;
+    k_tri_keys<<<(unsigned)std::max<i64>(1, std::min<i64>((groups + 7) / 8, (i64)ctx->sms * 8)), 256, 0, ctx->stream>>>(ta);
+    k_sel_reset<<<1, 256, 0, ctx->stream>>>(ctx->d_state);
+    CU(cudaGetLastError());
+    i64 m = 0;
+    unsigned long long counters[2] = {0, 0};
+    if (kmax > 0) {
+        if ((rc = run_select(ctx, ctx->d_key1, nullptr, nullptr, NK, 0, kmax))) return rc;
+        // unpack into the output scratch arrays (reuse d_c_* as typed outputs)
+        i64* d_rank = ctx->d_c_idx; double* d_viol = ctx->d_o_score;
+        int8_t* d_type = (int8_t*)ctx->d_c_k1; int8_t* d_dens = (int8_t*)ctx->d_c_k2;
+        // m is only known on the device: unpack kmax slots, copy back the valid prefix
+        SelState hs;
+        CU(cudaMemcpyAsync(&hs, ctx->d_state, sizeof(SelState), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        m = std::min<i64>((i64)hs.out_count, kmax);
+        if (m > 0) {
+            k_tri_unpack<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(m, ctx->d_s_k1, ctx->d_s_idx, d_rank, d_type, d_viol, d_dens);
+            CU(cudaGetLastError());
+            if (out_triple_rank) CU(cudaMemcpyAsync(out_triple_rank, d_rank, m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            if (out_viol) CU(cudaMemcpyAsync(out_viol, d_viol, m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            if (out_type) CU(cudaMemcpyAsync(out_type, d_type, m, cudaMemcpyDeviceToHost, ctx->stream));
+            if (out_density) CU(cudaMemcpyAsync(out_density, d_dens, m, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
+    CU(cudaMemcpyAsync(counters, ctx->d_tri_counters, sizeof(counters), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *out_n = m;
+    if (out_n_violated) *out_n_violated = (int64_t)counters[1];
+    if (out_n_triples) *out_n_triples = (int64_t)counters[0];
+    return SDPCS_OK;
+}
+
+template <int D>
+static int launch_nn(sdpcs_ctx* ctx, const double* d_in, i64 m, double* d_out)
+{
+    const size_t smem = (size_t)score_full_smem_doubles<D>(FULL_WARPS) * sizeof(double);
+    auto kern = k_nn_eval<D, FULL_WARPS>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const i64 groups = (m + 31) / 32;
+    const unsigned grid = (unsigned)std::max<i64>(1, std::min<i64>((groups + FULL_WARPS - 1) / FULL_WARPS, ctx->sms));
+    kern<<<grid, FULL_WARPS * 32, smem, ctx->stream>>>(ctx->d_wfrag[D], d_in, m, d_out);
+    CU(cudaGetLastError());
+    return SDPCS_OK;
+}
+
+extern "C" int sdpcs_nn_eval(sdpcs_ctx* ctx, int rho, const double* inputs, int64_t m, double* out)
+{
+    if (!ctx || rho < 2 || rho > 5 || m < 0 || (m && (!inputs || !out))) return SDPCS_ERR_INVALID;
+    if (!ctx->d_wfrag[rho]) return ctx->fail(SDPCS_ERR_STATE, "NN weights not set for this rho");
+    if (m == 0) return SDPCS_OK;
+    CU(cudaSetDevice(ctx->device));
+    const int nin = rho * (rho + 3) / 2;
+    int rc = ensure_scratch(ctx, (size_t)m * (nin + 1) * 8);
+    if (rc) return rc;
+    double* d_in = (double*)ctx->d_scratch;
+    double* d_out = d_in + (size_t)m * nin;
+    CU(cudaMemcpyAsync(d_in, inputs, (size_t)m * nin * 8, cudaMemcpyHostToDevice, ctx->stream));
+    switch (rho) {
+    case 2: rc = launch_nn<2>(ctx, d_in, m, d_out); break;
+    case 3: rc = launch_nn<3>(ctx, d_in, m, d_out); break;
+    case 4: rc = launch_nn<4>(ctx, d_in, m, d_out); break;
+    default: rc = launch_nn<5>(ctx, d_in, m, d_out); break;
+    }
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out, d_out, (size_t)m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SDPCS_OK;
+}
+
+extern "C" int sdpcs_fp64_peak(sdpcs_ctx* ctx, double* dfma_tflops, double* dmma_tflops)
+{
+    if (!ctx) return SDPCS_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_scratch(ctx, 8192 * 8);
+    if (rc) return rc;
+    double* d = (double*)ctx->d_scratch;
+    std::vector<double> h(4096);
+    for (int i = 0; i < 4096; ++i) h[i] = 1e-3 / (1.0 + i % 7);
+    CU(cudaMemcpyAsync(d, h.data(), 4096 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const int iters = 8192, grid = ctx->sms * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    double best[2] = {0, 0};
+    for (int which = 0; which < 2; ++which)
+        for (int rep = 0; rep < 5; ++rep) {
+            CU(cudaEventRecord(e0, ctx->stream));
+            if (which == 0) k_peak_dfma<<<grid, threads, 0, ctx->stream>>>(d + 4096, d, iters);
+            else k_peak_dmma<<<grid, threads, 0, ctx->stream>>>(d + 4096, d, iters);
+            CU(cudaEventRecord(e1, ctx->stream));
+            CU(cudaEventSynchronize(e1));
+            float ms;
+            CU(cudaEventElapsedTime(&ms, e0, e1));
+            double fl = which == 0 ? 2.0 * 8 * iters * (double)grid * threads : 2.0 * 256 * 8 * iters * (double)grid * (threads / 32);
+            if (rep) best[which] = std::max(best[which], fl / ms * 1e-9);
+        }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (dfma_tflops) *dfma_tflops = best[0];
+    if (dmma_tflops) *dmma_tflops = best[1];
+    return SDPCS_OK;
+}

@@ -1,0 +1,245 @@
+// Device-side building blocks of the cut-selection path (sm_100a):
+//   K1  lexicographic subset unranking / advancing (replaces the nested loops of cut_select_qp.py:451-455 and
+//       the stored agg_list of :524-540 -- no index list is kept in HBM in all-subsets mode)
+//   K3  register-resident cyclic-Jacobi symmetric eigensolver for orders 3..6 in FP64
+//       (replaces np.linalg.eigvalsh/eigh(M, "U") at cut_select_qp.py:796-797)
+//   tansig(n) = 2/(1+exp(-2n))-1 (neural_net_3D.m:76-78) in 13 FP64-pipe operations
+//   DMMA.8x8x4 wrapper (mma.sync.m8n8k4.f64), the native FP64 tensor shape on sm_100a
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+typedef unsigned long long u64;
+typedef long long i64;
+
+namespace sdpcs {
+
+// ---------------------------------------------------------------------------------------------------
+// combinatorics
+// ---------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ u64 binom_small(int m, int j)
+{
+    // C(m, j) for j <= 5, m <= 250 (C(250,5) = 7.8e9; the products below stay < 2^63)
+    if (m < j) return 0;
+    u64 M = (u64)m;
+    switch (j) {
+    case 0: return 1;
+    case 1: return M;
+    case 2: return M * (M - 1) / 2;
+    case 3: return M * (M - 1) * (M - 2) / 6;
+    case 4: return M * (M - 1) * (M - 2) * (M - 3) / 24;
+    default: return M * (M - 1) * (M - 2) * (M - 3) / 24 * (M - 4) / 5;
+    }
+}
+
+// rank -> ascending tuple in lexicographic order (= itertools.combinations order). O(n + D) steps.
+template <int D>
+__host__ __device__ __forceinline__ void lex_unrank(int n, u64 r, int (&c)[D])
+{
+    int v = 0;
+#pragma unroll
+    for (int j = 1; j <= D; ++j) {
+        while (true) {
+            u64 cnt = binom_small(n - 1 - v, D - j);
+            if (r < cnt) break;
+            r -= cnt;
+            ++v;
+        }
+        c[j - 1] = v;
+        ++v;
+    }
+}
+
+// Move `delta` positions forward in lexicographic order (delta small, e.g. 32). Returns false once the
+// end of the enumeration is passed (c is then left at a valid but meaningless tuple).
+template <int D>
+__device__ __forceinline__ bool lex_advance(int n, int (&c)[D], int delta)
+{
+    int rem = delta;
+    while (true) {
+        int room = (n - 1) - c[D - 1];
+        if (rem <= room) {
+            c[D - 1] += rem;
+            return true;
+        }
+        rem -= room + 1;
+        bool done = false;
+#pragma unroll
+        for (int j = D - 2; j >= 0; --j) {
+            if (!done && c[j] < n - D + j) {
+                ++c[j];
+#pragma unroll
+                for (int t = j + 1; t < D; ++t) c[t] = c[t - 1] + 1;
+                done = true;
+            }
+        }
+        if (!done) {
+#pragma unroll
+            for (int t = 0; t < D; ++t) c[t] = t;
+            return false;
+        }
+    }
+}
+
+// flat upper-triangular index of (i, j), i <= j: n*i - i(i+1)/2 + j   (cut_select_qp.py:531)
+__host__ __device__ __forceinline__ int tri_index(int n, int i, int j) { return n * i - ((i * (i + 1)) >> 1) + j; }
+
+// ---------------------------------------------------------------------------------------------------
+// order-preserving double <-> u64 key (larger double -> larger key); key 0 is reserved for "excluded"
+// ---------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ u64 enc_key(double x)
+{
+    u64 b;
+#ifdef __CUDA_ARCH__
+    b = (u64)__double_as_longlong(x);
+#else
+    memcpy(&b, &x, 8);
+#endif
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__host__ __device__ __forceinline__ double dec_key(u64 k)
+{
+    u64 b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((long long)b);
+#else
+    double x;
+    memcpy(&x, &b, 8);
+    return x;
+#endif
+}
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------------
+// K3: cyclic Jacobi, order M, fully unrolled so the matrix lives in registers.
+// a[i][j] is used for i <= j only. On return the diagonal holds the eigenvalues (unsorted).
+// ---------------------------------------------------------------------------------------------------
+template <int M, bool VEC>
+__device__ __forceinline__ void jacobi_sweeps(double (&a)[M][M], double (&v)[M][M], int sweeps)
+{
+    if (VEC) {
+#pragma unroll
+        for (int i = 0; i < M; ++i)
+#pragma unroll
+            for (int j = 0; j < M; ++j) v[i][j] = (i == j) ? 1.0 : 0.0;
+    }
+#pragma unroll 1
+    for (int sw = 0; sw < sweeps; ++sw) {
+#pragma unroll
+        for (int p = 0; p < M - 1; ++p) {
+#pragma unroll
+            for (int q = p + 1; q < M; ++q) {
+                double apq = a[p][q];
+                if (apq != 0.0) {
+                    double app = a[p][p], aqq = a[q][q];
+                    double theta = (aqq - app) / (2.0 * apq);
+                    double t = copysign(1.0, theta) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
+                    double c = rsqrt(fma(t, t, 1.0));
+                    double s = t * c;
+                    double tau = s / (1.0 + c);
+                    a[p][p] = fma(-t, apq, app);
+                    a[q][q] = fma(t, apq, aqq);
+                    a[p][q] = 0.0;
+#pragma unroll
+                    for (int r = 0; r < M; ++r) {
+                        if (r != p && r != q) {
+                            // element (r,p) lives at a[min][max]
+                            double& arp = (r < p) ? a[r][p] : a[p][r];
+                            double& arq = (r < q) ? a[r][q] : a[q][r];
+                            double x = arp, y = arq;
+                            arp = fma(-s, fma(tau, x, y), x);
+                            arq = fma(s, fma(-tau, y, x), y);
+                        }
+                    }
+                    if (VEC) {
+#pragma unroll
+                        for (int r = 0; r < M; ++r) {
+                            double x = v[r][p], y = v[r][q];
+                            v[r][p] = fma(-s, fma(tau, x, y), x);
+                            v[r][q] = fma(s, fma(-tau, y, x), y);
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+__host__ __device__ __forceinline__ int default_sweeps(int m) { return m <= 4 ? 5 : 6; }
+
+// lam_min of [[1, x^T],[x, X]] for a subset of size D (matrix order D+1). Xs is the subset's upper
+// triangle in combinations_with_replacement order (cut_select_qp.py:530, 792-794).
+template <int D>
+__device__ __forceinline__ double lam_min_subset(const double (&xs)[D], const double (&Xs)[D * (D + 1) / 2], int sweeps)
+{
+    constexpr int M = D + 1;
+    double a[M][M], v[1][1];
+    (void)v;
+    a[0][0] = 1.0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) a[0][i + 1] = xs[i];
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = i; j < D; ++j) a[i + 1][j + 1] = Xs[k++];
+    double dummy[M][M];
+    jacobi_sweeps<M, false>(a, dummy, sweeps);
+    double lam = a[0][0];
+#pragma unroll
+    for (int i = 1; i < M; ++i) lam = fmin(lam, a[i][i]);
+    return lam;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// DMMA.8x8x4 : D(8x8) += A(8x4, row) * B(4x8, col), FP64.  Fragment ownership (lane = 4*g + t):
+//   a = A[g][t], b = B[t][g], c0 = C[g][2t], c1 = C[g][2t+1]
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b)
+{
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// tansig from the pre-scaled pre-activation zs = -2*log2(e)*n:  2/(1 + 2^zs) - 1  (= tanh(n)).
+// 2^w with w = -|zs|: 8-bit table (T[j] = 2^(j/256), shared memory) + degree-4 polynomial; the reciprocal of
+// d = 1 + 2^w in (1, 2] starts from an FP32 MUFU.RCP seed (bit-cast, no FP64 conversion instructions) refined
+// by one cubic step. 13 FP64-pipe operations; max abs error 3.6e-16 (same as the reference formula with libm exp).
+// ---------------------------------------------------------------------------------------------------
+#define SDPCS_TANSIG_SCALE (-2.8853900817779268147)  /* -2*log2(e) */
+__device__ __forceinline__ double tansig_scaled(double zs, const double* __restrict__ T)
+{
+    const double A1 = 0.6931471805599453094, A2 = 0.2402265069591007123, A3 = 0.0555041086648215800,
+                 A4 = 0.0096181291076284772;
+    const double MAGIC = 26388279066624.0;  // 1.5 * 2^44: ulp = 2^-8
+    int hi = __double2hiint(zs);
+    int sgn = hi & 0x80000000;
+    double w = __hiloint2double(hi | 0x80000000, __double2loint(zs));
+    if ((hi & 0x7fffffff) > 0x408F4000) w = -1000.0;
+    double kf = w + MAGIC;
+    int i = __double2loint(kf);
+    double s = w - (kf - MAGIC);
+    double q = fma(A4, s, A3);
+    q = fma(q, s, A2);
+    q = fma(q, s, A1);
+    double p = q * s;
+    double Tj = T[i & 255];
+    double t0 = fma(Tj, p, Tj);
+    double t = __hiloint2double(__double2hiint(t0) + ((i >> 8) << 20), __double2loint(t0));
+    double d = 1.0 + t;
+    unsigned fb = ((unsigned)(__double2hiint(d) - 0x38000000) << 3) | ((unsigned)__double2loint(d) >> 29);
+    float yf;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"(__uint_as_float(fb)));
+    unsigned yb = __float_as_uint(yf);
+    double y0 = __hiloint2double((int)((yb >> 3) + 0x38000000u), (int)(yb << 29));
+    double e = fma(-d, y0, 1.0);
+    double e2 = fma(e, e, e);
+    double y = fma(y0, e2, y0);
+    double r = fma(2.0, y, -1.0);
+    return __hiloint2double(__double2hiint(r) ^ (sgn ^ 0x80000000), __double2loint(r));
+}
+#endif  // __CUDACC__
+
+}  // namespace sdpcs

@@ -1,0 +1,258 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against the
+oracle on the same inputs and against the golden fixtures produced by the unmodified reference.
+
+Tolerances (north_star): selected indices and order bit-exact; eigenvalues 1e-9 relative (we assert 1e-12
+absolute, the matrices have O(1) entries); NN-based scores 1e-5 (we assert 1e-9 absolute)."""
+import numpy as np
+import pytest
+
+from conftest import inst_arrays
+from oracle import cutsel_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+LAM_TOL = 1e-12
+OBJ_TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def capi():
+    import sdpcutsel_via_nn_b200 as pkg
+    return pkg._capi
+
+
+def make_engine(capi, blobs, n, Q_arr, rhos=(2, 3, 4, 5)):
+    eng = capi.Engine(0)
+    for d in rhos:
+        eng.set_weights(d, blobs[d])
+    eng.set_instance(n, Q_arr)
+    return eng
+
+
+def _sets(idx):
+    return [tuple(int(v) for v in r if v >= 0) for r in idx]
+
+
+@pytest.mark.parametrize("d", [2, 3, 4, 5])
+def test_nn_eval_vs_NNs_so(capi, blobs, golden, d):
+    eng = capi.Engine(0)
+    eng.set_weights(d, blobs[d])
+    y = eng.nn_eval(d, golden["nn%d_in" % d])
+    assert np.abs(y - golden["nn%d_out" % d]).max() < 1e-11
+
+
+def test_unrank_matches_itertools(capi):
+    for n, rho in [(30, 3), (20, 4), (17, 5), (250, 2)]:
+        want = orc.cover_all(n, rho)
+        got = capi.unrank(n, rho, np.arange(want.shape[0]))
+        assert np.array_equal(got, want)
+        assert capi.binom(n, rho) == want.shape[0]
+    assert capi.binom(250, 5) == 7817031300
+
+
+def test_cfg1_all_triples(capi, blobs, golden):
+    n, Q_arr, adj = inst_arrays(golden, "spar030-060-1")
+    eng = make_engine(capi, blobs, n, Q_arr)
+    eng.set_cover_all(3)
+    assert eng.num_candidates == 4060
+    vv = golden["cfg1_vars"]
+    idx = orc.cover_all(n, 3)
+    lam_o, obj_o = orc.score_cover(Q_arr, n, idx, np.full(4060, 3), vv, blobs)
+    eng.score(vv, 3)
+    lam, obj = eng.scores()
+    assert np.abs(lam - lam_o).max() < LAM_TOL
+    assert np.abs(obj - obj_o).max() < OBJ_TOL
+    k = 406
+    r = eng.select(1, vv, 5000)                      # strat 1: whole violated list
+    assert _sets(idx[r["idx"]]) == _sets(golden["cfg1_s1_sets"])
+    assert np.abs(r["score"] - golden["cfg1_s1_score"]).max() < LAM_TOL
+    r = eng.select(2, vv, 4060)                      # strat 2: the complete ranking
+    assert np.array_equal(r["idx"], golden["cfg1_s2_idx"])
+    assert np.abs(r["score"] - golden["cfg1_s2_score"]).max() < OBJ_TOL
+    r = eng.select(4, vv, k)
+    assert r["new_strat"] == int(golden["cfg1_s4_newstrat"])
+    assert np.array_equal(r["idx"], golden["cfg1_s4_idx"][:k])
+    assert np.abs(r["score"] - golden["cfg1_s4_score"][:k]).max() < OBJ_TOL
+    # combined rule where fewer strong cuts than k exist: the whole list is walked
+    ns, order, score = orc.select_comb(obj_o, lam_o, 3000)
+    r = eng.select(4, vv, 3000)
+    assert r["new_strat"] == ns and np.array_equal(r["idx"], order[:3000])
+    assert np.abs(r["score"] - score[:3000]).max() < OBJ_TOL
+
+
+def test_cfg1_eigcuts(capi, blobs, golden):
+    n, Q_arr, adj = inst_arrays(golden, "spar030-060-1")
+    eng = make_engine(capi, blobs, n, Q_arr, rhos=())
+    vv = golden["cfg1_vars"]
+    sets = golden["cfg1_s1_sets"][:406]
+    ind, val, rhs, lam, viol = eng.gen_cuts(3, sets, vv)
+    assert viol.all()
+    assert np.array_equal(ind, golden["cfg1_s1_cut_ind"])
+    # eigenvector sign is arbitrary but the cut coefficients are products -> sign free
+    assert np.abs(val - golden["cfg1_s1_cut_val"]).max() < 1e-9
+    assert np.abs(rhs - golden["cfg1_s1_cut_rhs"]).max() < 1e-9
+    assert np.abs(-lam - golden["cfg1_s1_score"][:406]).max() < LAM_TOL
+    # eigendecomp entry point vs LAPACK on one subset
+    X_vals, x_vals = orc.split_vars(vv, n)
+    s = [int(v) for v in sets[0]]
+    Xs = X_vals[orc.xarr_inds(n, s)]
+    w, V = eng.eigendecomp(3, x_vals[s], Xs)
+    M = orc.eig_matrix(x_vals[s][None, :], Xs[None, :])[0]
+    w_ref = np.linalg.eigvalsh(M, "U")
+    assert np.abs(w - w_ref).max() < 1e-13
+    Mfull = np.triu(M) + np.triu(M, 1).T
+    assert np.abs(Mfull @ V - V * w[None, :]).max() < 1e-12
+
+
+@pytest.mark.parametrize("dim", [3, 4, 5])
+def test_mixed_size_cover(capi, blobs, golden, dim):
+    n, Q_arr, adj = inst_arrays(golden, "spar040-030-1")
+    idx, sizes = orc.cover_pattern_E(adj, dim)
+    eng = make_engine(capi, blobs, n, Q_arr)
+    eng.set_cover_list(dim, idx)
+    vv = golden["mix_vars"]
+    N = idx.shape[0]
+    k = max(1, min(int(np.floor(0.1 * N)), 5000))
+    lam_o, obj_o = orc.score_cover(Q_arr, n, idx, sizes, vv, blobs)
+    eng.score(vv, 3)
+    lam, obj = eng.scores()
+    assert np.abs(lam - lam_o).max() < LAM_TOL and np.abs(obj - obj_o).max() < OBJ_TOL
+    r = eng.select(1, vv, N)
+    assert _sets(idx[r["idx"]]) == _sets(golden["mix_d%d_s1_sets" % dim])
+    r = eng.select(2, vv, N)
+    assert np.array_equal(r["idx"], golden["mix_d%d_s2_idx" % dim])
+    r = eng.select(4, vv, k)
+    assert r["new_strat"] == int(golden["mix_d%d_s4_newstrat" % dim])
+    assert np.array_equal(r["idx"], golden["mix_d%d_s4_idx" % dim][:k])
+    assert np.abs(r["score"] - golden["mix_d%d_s4_score" % dim][:k]).max() < OBJ_TOL
+    # cuts for the optimality selection, mixed subset sizes in one call
+    top = golden["mix_d%d_s2_idx" % dim][:k]
+    ind, val, rhs, lamc, viol = eng.gen_cuts(dim, idx[top], vv)
+    want_ind, want_val, want_rhs = (golden["mix_d%d_s2_cut_%s" % (dim, s)] for s in ("ind", "val", "rhs"))
+    assert int(viol.sum()) == want_rhs.shape[0]
+    assert np.array_equal(ind[viol], want_ind)
+    assert np.abs(val[viol] - want_val).max() < 1e-9 and np.abs(rhs[viol] - want_rhs).max() < 1e-9
+
+
+def test_cfg2_spar125_pattern_E_and_triangles(capi, blobs, golden):
+    n, Q_arr, adj = inst_arrays(golden, "spar125-075-1")
+    idx, sizes = orc.cover_pattern_E(adj, 3)
+    eng = make_engine(capi, blobs, n, Q_arr)
+    eng.set_cover_list(3, idx)
+    vv = golden["cfg2_vars"]
+    k = 5000
+    r = eng.select(1, vv, k)
+    assert _sets(idx[r["idx"]]) == _sets(golden["cfg2_s1_sets"])
+    assert np.abs(r["score"] - golden["cfg2_s1_score"]).max() < LAM_TOL
+    assert int(r["counts"][1]) == int(golden["cfg2_s1_len"])          # number of violated subsets
+    r = eng.select(2, vv, k)
+    assert np.array_equal(r["idx"], golden["cfg2_s2_idx"])
+    assert np.abs(r["score"] - golden["cfg2_s2_score"]).max() < OBJ_TOL
+    r = eng.select(4, vv, k)
+    assert r["new_strat"] == int(golden["cfg2_s4_newstrat"])
+    assert np.array_equal(r["idx"], golden["cfg2_s4_idx"])
+    assert np.abs(r["score"] - golden["cfg2_s4_score"]).max() < OBJ_TOL
+    # triangles: bit-exact (adds only)
+    eng.set_tri_pattern(adj)
+    t = eng.triangles(vv, 10000)
+    tri, dens = orc.triangles_pre(adj, n)
+    pos, typ, viol = orc.triangles_sep(n, tri, dens, vv, 0.1)
+    assert t["n_triples"] == tri.shape[0] == int(golden["cfg2_tri_ntriples"])
+    assert t["rank"].shape[0] == 10000
+    got_tri = capi.unrank(n, 3, t["rank"])
+    assert np.array_equal(got_tri, tri[pos]) and np.array_equal(t["type"], typ)
+    assert np.array_equal(t["viol"], viol)                              # bit-exact
+    for i in (0, 1, 5000, 9999):
+        ind, val, rhs = orc.triangle_row(n, got_tri[i], int(t["type"][i]))
+        m = len(ind)
+        assert ind == list(golden["cfg2_tri_ind"][i][:m]) and rhs == golden["cfg2_tri_rhs"][i]
+
+
+@pytest.mark.parametrize("dim", [3, 4, 5])
+def test_qcqp_all_subsets(capi, blobs, golden, dim):
+    n = 20
+    Q_arr = golden["qcqp_Q_arr"]
+    eng = make_engine(capi, blobs, n, Q_arr)
+    eng.set_cover_all(dim)
+    N = eng.num_candidates
+    assert N == int(golden["qcqp_d%d_N" % dim][0])
+    vv = golden["qcqp_vars"]
+    k = max(1, min(int(np.floor(0.1 * N)), 5000))
+    idx = orc.cover_all(n, dim)
+    r = eng.select(1, vv, k)
+    assert _sets(idx[r["idx"]]) == _sets(golden["qcqp_d%d_s1_sets" % dim])
+    assert np.abs(r["score"] - golden["qcqp_d%d_s1_score" % dim]).max() < LAM_TOL
+    r = eng.select(4, vv, k)
+    assert r["new_strat"] == int(golden["qcqp_d%d_s4_newstrat" % dim])
+    assert np.array_equal(r["idx"], golden["qcqp_d%d_s4_idx" % dim])
+    assert np.abs(r["score"] - golden["qcqp_d%d_s4_score" % dim]).max() < OBJ_TOL
+
+
+@pytest.mark.parametrize("n,rho,density", [(40, 5, 0.75), (60, 4, 0.5), (125, 3, 0.75)])
+def test_all_subsets_vs_oracle_medium(capi, blobs, n, rho, density):
+    """Synthetic instances (SURVEY 8d recipe), hundreds of thousands of candidates, both scores + top-k."""
+    Q_arr, adj = orc.boxqp_arrays(orc.synth_instance(n, density, seed=7))
+    vv = orc.synth_point(n, seed=8)
+    eng = make_engine(capi, blobs, n, Q_arr)
+    eng.set_cover_all(rho)
+    N = eng.num_candidates
+    idx = orc.cover_all(n, rho)
+    assert N == idx.shape[0]
+    lam_o, obj_o = orc.score_cover(Q_arr, n, idx, np.full(N, rho), vv, blobs)
+    eng.score(vv, 3)
+    lam, obj = eng.scores()
+    assert np.abs(lam - lam_o).max() < LAM_TOL and np.abs(obj - obj_o).max() < OBJ_TOL
+    k = 5000
+    order, score = orc.select_feas(lam_o)
+    r = eng.select(1, vv, k)
+    assert np.array_equal(r["idx"], order[:k])
+    order, score = orc.select_opt(obj_o)
+    r = eng.select(2, vv, k)
+    assert np.array_equal(r["idx"], order[:k])
+    ns, order, score = orc.select_comb(obj_o, lam_o, k)
+    r = eng.select(4, vv, k)
+    assert r["new_strat"] == ns and np.array_equal(r["idx"], order[:k])
+    # sharded rank ranges reproduce the same scores (multi-GPU partitioning, one shard at a time)
+    cut = N // 3 + 7
+    eng.set_cover_all(rho, cut, N)
+    eng.score(vv, 3)
+    lam2, obj2 = eng.scores()
+    assert np.array_equal(lam2, lam[cut:]) and np.array_equal(obj2, obj[cut:])
+
+
+def test_degenerate_vertex_ties(capi, blobs, golden):
+    """x = 0.5, X in {0, 0.5}: massive exact ties. Scores within tolerance; ties resolved by ascending index."""
+    n, Q_arr, adj = inst_arrays(golden, "spar030-060-1")
+    eng = make_engine(capi, blobs, n, Q_arr)
+    eng.set_cover_all(3)
+    vd = orc.degenerate_point(n, Q_arr)
+    eng.score(vd, 1)
+    lam, _ = eng.scores(obj=False)
+    idx = orc.cover_all(n, 3)
+    lam_o, _ = orc.score_cover(Q_arr, n, idx, np.full(4060, 3), vd, want_obj=False)
+    assert np.abs(lam - lam_o).max() < LAM_TOL
+    r = eng.select(1, vd, 4060)
+    viol = lam < -1e-15
+    assert r["idx"].shape[0] == int(viol.sum())
+    # the GPU order is exactly (own score desc, index asc)
+    want = np.lexsort((np.arange(4060)[viol], lam[viol]))
+    assert np.array_equal(r["idx"], np.arange(4060)[viol][want])
+
+
+def test_errors_are_loud(capi, blobs):
+    eng = capi.Engine(0)
+    with pytest.raises(capi.SdpcsError):
+        eng.set_cover_all(3)                       # no instance
+    eng.set_instance(10, np.zeros(55))
+    with pytest.raises(capi.SdpcsError):
+        eng.set_weights(3, blobs[4])               # wrong net
+    eng.set_cover_all(3)
+    with pytest.raises(capi.SdpcsError):
+        eng.score(np.zeros(65), 2)                 # NN weights missing
+    with pytest.raises(capi.SdpcsError):
+        eng.set_cover_list(3, np.array([[3, 2, 1]], dtype=np.int16))
+    # empty / tiny covers
+    eng.set_cover_list(3, np.zeros((0, 3), dtype=np.int16))
+    assert eng.num_candidates == 0
+    r = eng.select(1, np.zeros(65), 10)
+    assert r["idx"].size == 0
