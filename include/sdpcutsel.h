@@ -88,7 +88,8 @@ int sdpcs_num_candidates(const sdpcs_ctx *ctx, int64_t *N);
 /* Score every candidate of the cover at the LP point vars_values = [X upper-tri row-major | x]
  * (cut_select_qp.py:547).  want bit 0: lam_min of [1 x^T; x X]_rho (cut_select_qp.py:643-647, 788-797);
  * bit 1: optimality measure max_elem*(NN(x_rho, Q~_rho) - <Q~_rho, X_rho>) (cut_select_qp.py:573-582).
- * Scores stay resident on the device for sdpcs_topk / sdpcs_scores. */
+ * Scores stay resident on the device for sdpcs_topk / sdpcs_scores.  vars_values == NULL re-uses the LP point
+ * already resident on the device from the previous call (device-resident timing). */
 int sdpcs_score(sdpcs_ctx *ctx, const double *vars_values, int want);
 
 /* Copy resident scores of local candidates [i0, i1) to the host (either pointer may be NULL). Parity tests. */
@@ -116,7 +117,7 @@ int sdpcs_merge_topk(sdpcs_ctx *ctx, int64_t m, const double *score, const doubl
 /* One-call selection on a single GPU with HOST buffers (upload + score + select + download):
  * the whole of _sel_eigcut_by_ordering_on_measure (cut_select_qp.py:543-654) for strat 1, 2, 4, returning the
  * prefix of length <= k of the ranked list.  out_counts = {N, #violated walked, #strong}; out_new_strat as
- * cut_select_qp.py:629 (strat 4 only, else = strat). */
+ * cut_select_qp.py:629 (strat 4 only, else = strat).  vars_values == NULL: use the resident LP point. */
 int sdpcs_select(sdpcs_ctx *ctx, int strat, const double *vars_values, int64_t k,
                  int64_t *out_idx, double *out_score, double *out_lam, double *out_obj,
                  int64_t *out_n, int64_t *out_counts, int *out_new_strat);

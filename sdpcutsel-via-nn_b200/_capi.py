@@ -136,10 +136,16 @@ class Engine(object):
         return N.value
 
     # -- scoring / selection -----------------------------------------------------------------------
-    def score(self, vars_values, want=3):
+    def _vars(self, vars_values):
+        if vars_values is None:          # re-use the LP point resident on the device
+            return None
         v = _f64(vars_values)
         if v.size != self.n * (self.n + 1) // 2 + self.n:
             raise ValueError("vars_values must hold n(n+1)/2 + n values")
+        return v
+
+    def score(self, vars_values, want=3):
+        v = self._vars(vars_values)
         self._ck(self._lib.sdpcs_score(self._ctx, _ptr(v), c_int(want)))
 
     def scores(self, i0=0, i1=None, lam=True, obj=True):
@@ -175,9 +181,7 @@ class Engine(object):
 
     def select(self, strat, vars_values, k):
         """One-call selection with host buffers. Returns dict(idx, score, lam, obj, counts, new_strat)."""
-        v = _f64(vars_values)
-        if v.size != self.n * (self.n + 1) // 2 + self.n:
-            raise ValueError("vars_values must hold n(n+1)/2 + n values")
+        v = self._vars(vars_values)
         k = int(k)
         kk = max(k, 1)
         idx, sc, lam, obj = np.empty(kk, np.int64), np.empty(kk), np.empty(kk), np.empty(kk)

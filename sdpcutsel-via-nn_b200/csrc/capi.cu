@@ -53,6 +53,7 @@ struct sdpcs_ctx {
     // triangles
     uint8_t* d_adj = nullptr;
     bool have_adj = false;
+    bool vars_resident = false;
     unsigned long long* d_tri_counters = nullptr;
     // generic scratch
     void* d_scratch = nullptr;
@@ -302,6 +303,7 @@ extern "C" int sdpcs_set_instance(sdpcs_ctx* ctx, int n, const double* Q_arr)
     ctx->n = n;
     ctx->mode = 0; ctx->N = 0; ctx->have = 0;
     ctx->have_adj = false;
+    ctx->vars_resident = false;
     return SDPCS_OK;
 }
 
@@ -417,6 +419,7 @@ static int upload_vars(sdpcs_ctx* ctx, const double* vars_values)
     CU(cudaMemcpyAsync(ctx->d_vars, ctx->h_vars, len * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaEventRecord(ctx->ev[5], ctx->stream));
     ctx->ev_h2d = true;
+    ctx->vars_resident = true;
     return SDPCS_OK;
 }
 
@@ -491,11 +494,13 @@ static int score_device(sdpcs_ctx* ctx, int want)
 
 extern "C" int sdpcs_score(sdpcs_ctx* ctx, const double* vars_values, int want)
 {
-    if (!ctx || !vars_values) return SDPCS_ERR_INVALID;
+    if (!ctx) return SDPCS_ERR_INVALID;
     if (!ctx->mode) return ctx->fail(SDPCS_ERR_STATE, "cover not set");
     CU(cudaSetDevice(ctx->device));
-    int rc = upload_vars(ctx, vars_values);
-    if (rc) return rc;
+    if (vars_values) {
+        int rc = upload_vars(ctx, vars_values);
+        if (rc) return rc;
+    } else if (!ctx->vars_resident) return ctx->fail(SDPCS_ERR_STATE, "vars_values == NULL but no LP point is resident");
     return score_device(ctx, want);
 }
 
@@ -643,13 +648,15 @@ extern "C" int sdpcs_select(sdpcs_ctx* ctx, int strat, const double* vars_values
                             double* out_score, double* out_lam, double* out_obj, int64_t* out_n, int64_t* out_counts,
                             int* out_new_strat)
 {
-    if (!ctx || !vars_values) return SDPCS_ERR_INVALID;
+    if (!ctx) return SDPCS_ERR_INVALID;
     if (strat != 1 && strat != 2 && strat != 4) return ctx->fail(SDPCS_ERR_INVALID, "strat must be 1, 2 or 4");
     if (!ctx->mode) return ctx->fail(SDPCS_ERR_STATE, "cover not set");
     CU(cudaSetDevice(ctx->device));
     k = std::min<i64>(std::max<i64>(k, 0), ctx->N);       // sel_size = min(sel_size, len(agg_list)), cut_select_qp.py:550
-    int rc = upload_vars(ctx, vars_values);
-    if (rc) return rc;
+    int rc = SDPCS_OK;
+    if (vars_values) {
+        if ((rc = upload_vars(ctx, vars_values))) return rc;
+    } else if (!ctx->vars_resident) return ctx->fail(SDPCS_ERR_STATE, "vars_values == NULL but no LP point is resident");
     if ((rc = score_device(ctx, strat == 1 ? 1 : strat == 2 ? 2 : 3))) return rc;
     int new_strat = strat;
     i64 counts[3] = {ctx->N, 0, 0};

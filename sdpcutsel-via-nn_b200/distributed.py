@@ -1,0 +1,99 @@
+"""Multi-GPU selection: the candidate index space is cut into contiguous rank ranges, one per process/GPU
+(torch.distributed, NCCL over NVLink on the B200 box, gloo in CPU tests). Each rank scores its shard and takes a
+local top-k; one small all-gather (k x 4 doubles per rank) plus an identical merge on every rank gives the
+global selection. The combined strategy needs the global pivot, hence two gather rounds and one
+all-reduce of three counters.
+"""
+import numpy as np
+
+
+def shard_range(N, world, rank):
+    return rank * N // world, (rank + 1) * N // world
+
+
+class ShardedSelector(object):
+    """engine: an _capi.Engine (or any object with score/topk/counts/merge_topk) whose cover is this rank's shard."""
+
+    def __init__(self, engine, group=None, device=None):
+        self.eng = engine
+        self.group = group
+        self.device = device
+        try:
+            import torch.distributed as dist
+            self.dist = dist if dist.is_available() and dist.is_initialized() else None
+        except ImportError:
+            self.dist = None
+        self.world = self.dist.get_world_size(group) if self.dist else 1
+
+    # -- collectives on small host arrays ------------------------------------------------------------
+    def _allgather(self, arr):
+        """arr: float64 (m, c) with the same shape on every rank -> (world, m, c)."""
+        if self.world == 1:
+            return arr[None]
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+        if self.device is not None:
+            t = t.to(self.device)
+        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out, t, group=self.group)
+        return out.cpu().numpy()
+
+    def _allreduce_sum(self, arr):
+        if self.world == 1:
+            return arr
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+        if self.device is not None:
+            t = t.to(self.device)
+        self.dist.all_reduce(t, group=self.group)
+        return t.cpu().numpy()
+
+    def _gather_merge(self, k, idx, score, lam, obj, use_obj2):
+        m = idx.shape[0]
+        pack = np.zeros((k + 1, 4))
+        pack[0, 0] = m
+        pack[1:m + 1, 0] = idx            # agg_idx < 2^44: exact in float64
+        pack[1:m + 1, 1] = score
+        pack[1:m + 1, 2] = lam
+        pack[1:m + 1, 3] = obj
+        allp = self._allgather(pack)
+        rows = np.concatenate([allp[r, 1:int(allp[r, 0, 0]) + 1] for r in range(self.world)], axis=0)
+        if rows.shape[0] == 0:
+            z = np.zeros(0)
+            return z.astype(np.int64), z, z, z
+        gidx = rows[:, 0].astype(np.int64)
+        if self.world == 1:
+            perm = np.arange(min(k, rows.shape[0]))
+        else:
+            perm = self.eng.merge_topk(rows[:, 1], rows[:, 3] if use_obj2 else None, gidx, k)
+        return gidx[perm], rows[perm, 1], rows[perm, 2], rows[perm, 3]
+
+    # -- public ------------------------------------------------------------------------------------
+    def select(self, strat, vars_values, k, n_total=None):
+        """Global selection over all shards. Returns dict(idx, score, lam, obj, counts, new_strat) -- identical
+        on every rank. vars_values None = LP point already resident on the device."""
+        eng = self.eng
+        k = int(k)
+        if strat not in (1, 2, 4):
+            raise ValueError("strat must be 1, 2 or 4")
+        eng.score(vars_values, 1 if strat == 1 else 2 if strat == 2 else 3)
+        if strat != 4:
+            idx, sc, lam, obj = eng.topk(strat, k)
+            counts = self._allreduce_sum(eng.counts().astype(np.float64)).astype(np.int64)
+            gi, gs, gl, go = self._gather_merge(k, idx, sc, lam, obj, False)
+            return dict(idx=gi, score=gs, lam=gl, obj=go, counts=counts, new_strat=strat)
+        idx, sc, lam, obj = eng.topk(3, k)
+        counts = self._allreduce_sum(eng.counts().astype(np.float64)).astype(np.int64)
+        N, n_viol, n_strong = (int(v) for v in counts)
+        k = min(k, N)
+        si, ss, _, so = self._gather_merge(k, idx, sc, lam, obj, False)
+        all_walked = n_strong < k or k == 0
+        pobj, pidx = (0.0, 0) if all_walked else (float(so[k - 1]), int(si[k - 1]))
+        idx, sc, lam, obj = eng.topk(4, k, pobj, pidx, 1 if all_walked else 0)
+        gi, gs, gl, go = self._gather_merge(k, idx, sc, lam, obj, True)
+        strong = min(n_strong, k)
+        viol_walked = n_viol if all_walked else k
+        new_strat = 4
+        if k > 0 and N > 0:
+            new_strat = 1 if strong / k < viol_walked / N else 4
+        return dict(idx=gi, score=gs, lam=gl, obj=go, counts=np.array([N, viol_walked, strong]), new_strat=new_strat)
