@@ -233,7 +233,7 @@ def main():
             e2e=dict(value=N * args.steps / (ms_e2e * 1e-3), unit="subsets/s", ms_per_step=ms_e2e / args.steps,
                      h2d_bytes_per_step=int(vv.size * 8), d2h_bytes_per_step=int((2 if args.strat == 4 else 1) * (k * 32 + 8288))),
             gpu_launches=int(launches),
-            roofline=dict(bound="tensor", kernel="k_score_full<5,true,8> (DMMA.8x8x4 FP64)" if rho == 5 else "k_score_full", achieved=achieved,
+            roofline=dict(bound="tensor", kernel="k_score_nn<%d,16> (DMMA.8x8x4 FP64 MLP) + k_score_feas<%d> (FP64 Jacobi)" % (rho, rho), achieved=achieved,
                           peak=peak["dmma_tflops"], unit="TFLOP/s", frac=achieved / peak["dmma_tflops"], traffic=traffic,
                           flops_per_subset=W, subsets_per_launch=n_local, kernel_ms=score_ms_step,
                           peak_source="FP64 DMMA.8x8x4 micro-benchmark run in this process (MEASURED_PEAKS.json has no FP64 entry); DFMA peak %.1f" % peak["dfma_tflops"]),

@@ -109,7 +109,7 @@ static int ensure_hout(sdpcs_ctx* ctx, size_t bytes)
 }
 
 // ---------------------------------------------------------------------------------------------------
-// NN weights: blob -> DMMA fragment order (see mlp16 in score_kernels.cuh)
+// NN weights: blob -> DMMA fragment order (see mlp8 in score_kernels.cuh)
 // ---------------------------------------------------------------------------------------------------
 template <int D>
 static bool pack_fragments(const double* blob, i64 len, std::vector<double>& out, std::string& err)
@@ -139,7 +139,7 @@ static bool pack_fragments(const double* blob, i64 len, std::vector<double>& out
         for (int nt = 0; nt < C::NT; ++nt)
             for (int lane = 0; lane < 32; ++lane) {
                 int g = lane >> 2, t = lane & 3, nrn = 8 * nt + g, k = 4 * ks + t;
-                out[C::OFF_W0 + (ks * C::NT + nt) * 32 + lane] = (nrn < h && k < n_in) ? s * W[0][nrn * n_in + k] : 0.0;
+                out[C::OFF_W0 + ks * C::NT * 32 + C::frag(nt, lane)] = (nrn < h && k < n_in) ? s * W[0][nrn * n_in + k] : 0.0;
             }
     for (int l = 1; l < C::NHID; ++l)
         for (int kt = 0; kt < C::NT; ++kt)
@@ -147,7 +147,7 @@ static bool pack_fragments(const double* blob, i64 len, std::vector<double>& out
                 for (int nt = 0; nt < C::NT; ++nt)
                     for (int lane = 0; lane < 32; ++lane) {
                         int g = lane >> 2, t = lane & 3, nrn = 8 * nt + g, k = 8 * kt + 2 * t + hh, ks = 2 * kt + hh;
-                        out[C::OFF_WH + (l - 1) * (2 * C::NT * C::NT * 32) + (ks * C::NT + nt) * 32 + lane] =
+                        out[C::OFF_WH + (l - 1) * C::LAYER + ks * C::NT * 32 + C::frag(nt, lane)] =
                             (nrn < h && k < h) ? s * W[l][nrn * h + k] : 0.0;
                     }
     for (int l = 0; l < C::NHID; ++l)
@@ -423,7 +423,7 @@ static int upload_vars(sdpcs_ctx* ctx, const double* vars_values)
     return SDPCS_OK;
 }
 
-constexpr int FULL_WARPS = 8;
+constexpr int NN_WARPS = 16;
 
 template <int D>
 static int launch_score(sdpcs_ctx* ctx, int want, const uint8_t* idx, const i64* pos, i64 N, i64 rank_begin)
@@ -435,31 +435,26 @@ static int launch_score(sdpcs_ctx* ctx, int want, const uint8_t* idx, const i64*
     a.wfrag = ctx->d_wfrag[D]; a.lam = ctx->d_lam; a.obj = ctx->d_obj;
     a.sweeps = ctx->params.jacobi_sweeps > 0 ? ctx->params.jacobi_sweeps : default_sweeps(D + 1);
     const i64 groups = (N + 31) / 32;
-    if (!(want & 2)) {
+    if (want & 1) {   // K1+K2+K3: lam_min of every candidate
         int occ = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_score_feas<D>, 256, 0));
         i64 grid = std::min<i64>((groups + 7) / 8, (i64)ctx->sms * std::max(occ, 1));
         k_score_feas<D><<<(unsigned)std::max<i64>(grid, 1), 256, 0, ctx->stream>>>(a);
-    } else {
-        if (!a.wfrag) return ctx->fail(SDPCS_ERR_STATE, "NN_" + std::to_string(D) + "D weights not set");
-        const size_t smem = (size_t)score_full_smem_doubles<D>(FULL_WARPS) * sizeof(double);
-        int occ = 0;
-        if (want & 1) {
-            auto kern = k_score_full<D, true, FULL_WARPS>;
-            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, FULL_WARPS * 32, smem));
-            i64 grid = std::min<i64>((groups + FULL_WARPS - 1) / FULL_WARPS, (i64)ctx->sms * std::max(occ, 1));
-            kern<<<(unsigned)std::max<i64>(grid, 1), FULL_WARPS * 32, smem, ctx->stream>>>(a);
-        } else {
-            auto kern = k_score_full<D, false, FULL_WARPS>;
-            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, FULL_WARPS * 32, smem));
-            i64 grid = std::min<i64>((groups + FULL_WARPS - 1) / FULL_WARPS, (i64)ctx->sms * std::max(occ, 1));
-            kern<<<(unsigned)std::max<i64>(grid, 1), FULL_WARPS * 32, smem, ctx->stream>>>(a);
-        }
+        CU(cudaGetLastError());
+        ctx->tm.score_launches++;
     }
-    CU(cudaGetLastError());
-    ctx->tm.score_launches++;
+    if (want & 2) {   // K1+K2+K4: optimality measure of every candidate
+        if (!a.wfrag) return ctx->fail(SDPCS_ERR_STATE, "NN_" + std::to_string(D) + "D weights not set");
+        const size_t smem = (size_t)score_nn_smem_doubles<D>(NN_WARPS) * sizeof(double);
+        auto kern = k_score_nn<D, NN_WARPS>;
+        int occ = 0;
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NN_WARPS * 32, smem));
+        i64 grid = std::min<i64>((groups + NN_WARPS - 1) / NN_WARPS, (i64)ctx->sms * std::max(occ, 1));
+        kern<<<(unsigned)std::max<i64>(grid, 1), NN_WARPS * 32, smem, ctx->stream>>>(a);
+        CU(cudaGetLastError());
+        ctx->tm.score_launches++;
+    }
     return SDPCS_OK;
 }
 
@@ -877,12 +872,12 @@ extern "C" int sdpcs_triangles(sdpcs_ctx* ctx, const double* vars_values, int64_
 template <int D>
 static int launch_nn(sdpcs_ctx* ctx, const double* d_in, i64 m, double* d_out)
 {
-    const size_t smem = (size_t)score_full_smem_doubles<D>(FULL_WARPS) * sizeof(double);
-    auto kern = k_nn_eval<D, FULL_WARPS>;
+    const size_t smem = (size_t)score_nn_smem_doubles<D>(NN_WARPS) * sizeof(double);
+    auto kern = k_nn_eval<D, NN_WARPS>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const i64 groups = (m + 31) / 32;
-    const unsigned grid = (unsigned)std::max<i64>(1, std::min<i64>((groups + FULL_WARPS - 1) / FULL_WARPS, ctx->sms));
-    kern<<<grid, FULL_WARPS * 32, smem, ctx->stream>>>(ctx->d_wfrag[D], d_in, m, d_out);
+    const unsigned grid = (unsigned)std::max<i64>(1, std::min<i64>((groups + NN_WARPS - 1) / NN_WARPS, ctx->sms));
+    kern<<<grid, NN_WARPS * 32, smem, ctx->stream>>>(ctx->d_wfrag[D], d_in, m, d_out);
     CU(cudaGetLastError());
     return SDPCS_OK;
 }

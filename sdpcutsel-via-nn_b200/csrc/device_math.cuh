@@ -111,8 +111,37 @@ __host__ __device__ __forceinline__ double dec_key(u64 k)
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------------
+// fast FP64 reciprocal / reciprocal square root: MUFU.RCP64H / MUFU.RSQ64H seed (~20 bits) + one cubic step.
+// No subnormal / zero / inf slow path: callers guarantee a normal positive argument.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double fast_rcp(double b)
+{
+    double y0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(b));
+    double e = fma(-b, y0, 1.0);
+    return fma(y0, fma(e, e, e), y0);
+}
+__device__ __forceinline__ double fast_rsqrt(double x)
+{
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    double t = x * y0;
+    double e = fma(-t, y0, 1.0);
+    double p = fma(0.375, e, 0.5);
+    return fma(y0 * e, p, y0);
+}
+// a / b with r = fast_rcp(b) shared by several quotients: one correction step on the residual.
+__device__ __forceinline__ double div_by(double a, double b, double r)
+{
+    double q = a * r;
+    return fma(fma(-q, b, a), r, q);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // K3: cyclic Jacobi, order M, fully unrolled so the matrix lives in registers.
 // a[i][j] is used for i <= j only. On return the diagonal holds the eigenvalues (unsorted).
+// Rotation (p,q) with b = a_pq, d = a_qq - a_pp:  t = sgn(d) 2b / (|d| + sqrt(d^2 + 4b^2)),
+// c = 1/sqrt(1+t^2), s = t c -- one rsqrt + one rcp + one rsqrt, 39 FP64 operations per rotation at M = 6.
 // ---------------------------------------------------------------------------------------------------
 template <int M, bool VEC>
 __device__ __forceinline__ void jacobi_sweeps(double (&a)[M][M], double (&v)[M][M], int sweeps)
@@ -129,34 +158,36 @@ __device__ __forceinline__ void jacobi_sweeps(double (&a)[M][M], double (&v)[M][
         for (int p = 0; p < M - 1; ++p) {
 #pragma unroll
             for (int q = p + 1; q < M; ++q) {
-                double apq = a[p][q];
-                if (apq != 0.0) {
-                    double app = a[p][p], aqq = a[q][q];
-                    double theta = (aqq - app) / (2.0 * apq);
-                    double t = copysign(1.0, theta) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
-                    double c = rsqrt(fma(t, t, 1.0));
-                    double s = t * c;
-                    double tau = s / (1.0 + c);
-                    a[p][p] = fma(-t, apq, app);
-                    a[q][q] = fma(t, apq, aqq);
+                const double b = a[p][q];
+                const double app = a[p][p], aqq = a[q][q];
+                const double d = aqq - app;
+                const double b2 = b + b;
+                const double S = fma(d, d, b2 * b2);
+                if (S > 1e-290 && b != 0.0) {
+                    const double h = S * fast_rsqrt(S);
+                    const double rd = fast_rcp(fabs(d) + h);
+                    const double t = copysign(b2 * rd, (d < 0.0) ? -b2 : b2);
+                    const double c = fast_rsqrt(fma(t, t, 1.0));
+                    const double s = t * c;
+                    a[p][p] = fma(-t, b, app);
+                    a[q][q] = fma(t, b, aqq);
                     a[p][q] = 0.0;
 #pragma unroll
                     for (int r = 0; r < M; ++r) {
                         if (r != p && r != q) {
-                            // element (r,p) lives at a[min][max]
                             double& arp = (r < p) ? a[r][p] : a[p][r];
                             double& arq = (r < q) ? a[r][q] : a[q][r];
-                            double x = arp, y = arq;
-                            arp = fma(-s, fma(tau, x, y), x);
-                            arq = fma(s, fma(-tau, y, x), y);
+                            const double x = arp, y = arq;
+                            arp = fma(-s, y, c * x);
+                            arq = fma(s, x, c * y);
                         }
                     }
                     if (VEC) {
 #pragma unroll
                         for (int r = 0; r < M; ++r) {
-                            double x = v[r][p], y = v[r][q];
-                            v[r][p] = fma(-s, fma(tau, x, y), x);
-                            v[r][q] = fma(s, fma(-tau, y, x), y);
+                            const double x = v[r][p], y = v[r][q];
+                            v[r][p] = fma(-s, y, c * x);
+                            v[r][q] = fma(s, x, c * y);
                         }
                     }
                 }
@@ -173,8 +204,7 @@ template <int D>
 __device__ __forceinline__ double lam_min_subset(const double (&xs)[D], const double (&Xs)[D * (D + 1) / 2], int sweeps)
 {
     constexpr int M = D + 1;
-    double a[M][M], v[1][1];
-    (void)v;
+    double a[M][M], dummy[M][M];
     a[0][0] = 1.0;
 #pragma unroll
     for (int i = 0; i < D; ++i) a[0][i + 1] = xs[i];
@@ -183,7 +213,6 @@ __device__ __forceinline__ double lam_min_subset(const double (&xs)[D], const do
     for (int i = 0; i < D; ++i)
 #pragma unroll
         for (int j = i; j < D; ++j) a[i + 1][j + 1] = Xs[k++];
-    double dummy[M][M];
     jacobi_sweeps<M, false>(a, dummy, sweeps);
     double lam = a[0][0];
 #pragma unroll

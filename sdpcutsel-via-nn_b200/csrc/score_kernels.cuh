@@ -38,9 +38,13 @@ struct NetCfg {
     static constexpr int KS0 = KIN / 4;
     static constexpr int STRIDE = (KIN % 16 == 4 || KIN % 16 == 12) ? KIN : KIN + 4; // conflict-free A loads
     // smem blob layout (doubles)
-    static constexpr int OFF_W0 = 0;                                   // [KS0][NT][32]
-    static constexpr int OFF_WH = OFF_W0 + KS0 * NT * 32;              // [NHID-1][2*NT][NT][32]
-    static constexpr int OFF_BIAS = OFF_WH + (NHID - 1) * 2 * NT * NT * 32;  // [NHID][HP]  (scaled)
+    // within a k-step the NT fragments are stored pairwise so one LDS.128 feeds two DMMAs:
+    //   frag(nt, lane) = (nt/2)*64 + lane*2 + (nt&1) for nt < 2*(NT/2), else (NT-1)*32 + lane
+    static constexpr int frag(int nt, int lane) { return nt < 2 * (NT / 2) ? (nt / 2) * 64 + lane * 2 + (nt & 1) : (NT - 1) * 32 + lane; }
+    static constexpr int OFF_W0 = 0;                                   // [KS0][frag(NT, lane)]
+    static constexpr int LAYER = 2 * NT * NT * 32;                     // doubles per hidden-layer weight block
+    static constexpr int OFF_WH = OFF_W0 + KS0 * NT * 32;              // [NHID-1][2*NT][frag(NT, lane)]
+    static constexpr int OFF_BIAS = OFF_WH + (NHID - 1) * LAYER;       // [NHID][HP]  (scaled)
     static constexpr int OFF_WOUT = OFF_BIAS + NHID * HP;              // [HP]
     static constexpr int OFF_XOFF = OFF_WOUT + HP;                     // [KIN]
     static constexpr int OFF_GAIN = OFF_XOFF + KIN;                    // [KIN]
@@ -112,122 +116,100 @@ __global__ void __launch_bounds__(256) k_score_feas(ScoreArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------------
-// MLP on 16 rows (subsets) of the warp's 32 via DMMA.8x8x4.
-//   stage : this warp's staging rows [32][STRIDE] holding the mapminmax'ed NN inputs (zero padded to KIN)
+// K4: NN_rhoD on 8 rows (subsets) per pass via DMMA.8x8x4, one rolled loop over the tansig layers.
+//   rows  : 8 staging rows [8][STRIDE] of this pass holding the mapminmax'ed NN inputs (zero padded to KIN)
 //   w     : the fragment-ordered weight blob in shared memory
 // Layer l+1 consumes the C fragments of layer l directly as A fragments: the C fragment of n-tile nt holds
 // columns 8nt+2t+{0,1} for lane (g,t), so k-step (nt,h) of the next layer is *defined* as the neuron set
 // {8nt+2t+h : t=0..3} and the weight fragments are pre-permuted accordingly on the host. Activations never
-// leave registers between layers.
-// Returns the two NN outputs (rows 8*0+g and 8+g of this pass) reduced across the quad, valid in every lane.
+// leave registers between layers; layer 0 takes its A fragments from the staging rows through the same
+// registers. The weights are pre-scaled by -2*log2(e) so the accumulator is directly the tansig argument.
+// Returns the NN output of row g, valid in all four lanes of the quad.
 // ---------------------------------------------------------------------------------------------------
 template <int D>
-__device__ __forceinline__ void mlp16(const double* __restrict__ w, const double* __restrict__ stage, int pass,
-                                      int lane, double (&yout)[2])
+__device__ __forceinline__ double mlp8(const double* __restrict__ w, const double* __restrict__ rows, int lane)
 {
     using C = NetCfg<D>;
     const int g = lane >> 2, t = lane & 3;
-    double acc[2][C::NT][2];
-    double act[2][C::NT][2];
+    double acc[C::NT][2];
+    double act[C::NT][2];
     const double* tab = w + C::OFF_TAB;
-
-    // ---- layer 0: A fragments from the staging rows
     {
-        const double* bias = w + C::OFF_BIAS;
+        const double* r = rows + g * C::STRIDE + t;
 #pragma unroll
-        for (int nt = 0; nt < C::NT; ++nt) {
-            double b0 = bias[8 * nt + 2 * t], b1 = bias[8 * nt + 2 * t + 1];
-            acc[0][nt][0] = b0; acc[0][nt][1] = b1;
-            acc[1][nt][0] = b0; acc[1][nt][1] = b1;
-        }
-        const double* r0 = stage + (16 * pass + g) * C::STRIDE + t;
-        const double* r1 = r0 + 8 * C::STRIDE;
-        const double* wf = w + C::OFF_W0 + lane;
+        for (int kt = 0; kt < C::NT; ++kt)
 #pragma unroll
-        for (int ks = 0; ks < C::KS0; ++ks) {
-            double a0 = r0[4 * ks], a1 = r1[4 * ks];
-#pragma unroll
-            for (int nt = 0; nt < C::NT; ++nt) {
-                double b = wf[(ks * C::NT + nt) * 32];
-                dmma884(acc[0][nt][0], acc[0][nt][1], a0, b);
-                dmma884(acc[1][nt][0], acc[1][nt][1], a1, b);
-            }
-        }
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-            for (int nt = 0; nt < C::NT; ++nt) {
-                act[mt][nt][0] = tansig_scaled(acc[mt][nt][0], tab);
-                act[mt][nt][1] = tansig_scaled(acc[mt][nt][1], tab);
-            }
+            for (int h = 0; h < 2; ++h) act[kt][h] = (2 * kt + h < C::KS0) ? r[4 * (2 * kt + h)] : 0.0;
     }
-    // ---- hidden layers 1..NHID-1: A fragments are the previous activations (registers)
 #pragma unroll 1
-    for (int l = 1; l < C::NHID; ++l) {
-        const double* bias = w + C::OFF_BIAS + l * C::HP;
+    for (int l = 0; l < C::NHID; ++l) {
+        const double2* bias = reinterpret_cast<const double2*>(w + C::OFF_BIAS + l * C::HP) + t;
 #pragma unroll
         for (int nt = 0; nt < C::NT; ++nt) {
-            double b0 = bias[8 * nt + 2 * t], b1 = bias[8 * nt + 2 * t + 1];
-            acc[0][nt][0] = b0; acc[0][nt][1] = b1;
-            acc[1][nt][0] = b0; acc[1][nt][1] = b1;
+            double2 b = bias[4 * nt];
+            acc[nt][0] = b.x; acc[nt][1] = b.y;
         }
-        const double* wf = w + C::OFF_WH + (l - 1) * (2 * C::NT * C::NT * 32) + lane;
+        const double* wl = w + ((l == 0) ? C::OFF_W0 : C::OFF_WH + (l - 1) * C::LAYER);
+        const int nks = (l == 0) ? C::KS0 : 2 * C::NT;
 #pragma unroll
         for (int kt = 0; kt < C::NT; ++kt) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int ks = 2 * kt + h;
-                double a0 = act[0][kt][h], a1 = act[1][kt][h];
+                if (ks < nks) {
+                    const double a = act[kt][h];
+                    const double* wk = wl + ks * (C::NT * 32);
 #pragma unroll
-                for (int nt = 0; nt < C::NT; ++nt) {
-                    double b = wf[(ks * C::NT + nt) * 32];
-                    dmma884(acc[0][nt][0], acc[0][nt][1], a0, b);
-                    dmma884(acc[1][nt][0], acc[1][nt][1], a1, b);
+                    for (int np = 0; np < C::NT / 2; ++np) {
+                        double2 b = reinterpret_cast<const double2*>(wk + np * 64)[lane];
+                        dmma884(acc[2 * np][0], acc[2 * np][1], a, b.x);
+                        dmma884(acc[2 * np + 1][0], acc[2 * np + 1][1], a, b.y);
+                    }
+                    if (C::NT & 1) {
+                        double b = wk[(C::NT - 1) * 32 + lane];
+                        dmma884(acc[C::NT - 1][0], acc[C::NT - 1][1], a, b);
+                    }
                 }
             }
         }
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-            for (int nt = 0; nt < C::NT; ++nt) {
-                act[mt][nt][0] = tansig_scaled(acc[mt][nt][0], tab);
-                act[mt][nt][1] = tansig_scaled(acc[mt][nt][1], tab);
-            }
+        for (int nt = 0; nt < C::NT; ++nt) {
+            act[nt][0] = tansig_scaled(acc[nt][0], tab);
+            act[nt][1] = tansig_scaled(acc[nt][1], tab);
+        }
     }
-    // ---- linear output layer + mapminmax_reverse (neural_net_3D.m:61-65, 81-85)
-    const double* wout = w + C::OFF_WOUT;
-    double y0 = 0.0, y1 = 0.0;
+    // linear output layer + mapminmax_reverse (neural_net_3D.m:61-65, 81-85)
+    const double2* wout = reinterpret_cast<const double2*>(w + C::OFF_WOUT) + t;
+    double y = 0.0;
 #pragma unroll
     for (int nt = 0; nt < C::NT; ++nt) {
-        double w0 = wout[8 * nt + 2 * t], w1 = wout[8 * nt + 2 * t + 1];
-        y0 = fma(w0, act[0][nt][0], y0); y0 = fma(w1, act[0][nt][1], y0);
-        y1 = fma(w0, act[1][nt][0], y1); y1 = fma(w1, act[1][nt][1], y1);
+        double2 wo = wout[4 * nt];
+        y = fma(wo.x, act[nt][0], y);
+        y = fma(wo.y, act[nt][1], y);
     }
-    y0 += __shfl_xor_sync(0xffffffffu, y0, 1); y1 += __shfl_xor_sync(0xffffffffu, y1, 1);
-    y0 += __shfl_xor_sync(0xffffffffu, y0, 2); y1 += __shfl_xor_sync(0xffffffffu, y1, 2);
+    y += __shfl_xor_sync(0xffffffffu, y, 1);
+    y += __shfl_xor_sync(0xffffffffu, y, 2);
     const double bout = w[C::OFF_MISC], y_gain = w[C::OFF_MISC + 1], y_xoff = w[C::OFF_MISC + 2];
-    yout[0] = ((bout + y0) - -1.0) / y_gain + y_xoff;
-    yout[1] = ((bout + y1) - -1.0) / y_gain + y_xoff;
+    return ((bout + y) - -1.0) / y_gain + y_xoff;
 }
 
-// ---------------------------------------------------------------------------------------------------
-// fused kernel: lam_min (optional) and the optimality measure for every candidate
-// ---------------------------------------------------------------------------------------------------
 template <int D>
-constexpr int score_full_smem_doubles(int warps) { return NetCfg<D>::BLOB + warps * (32 * NetCfg<D>::STRIDE + 32); }
+constexpr int score_nn_smem_doubles(int warps) { return NetCfg<D>::BLOB + warps * (32 * NetCfg<D>::STRIDE + 32); }
 
-template <int D, bool WANT_LAM, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 1) k_score_full(ScoreArgs a)
+// ---------------------------------------------------------------------------------------------------
+// optimality-measure kernel: obj = max_elem * (NN(x_rho, Q~_rho) - <Q~_rho, X_rho>) for every candidate
+// ---------------------------------------------------------------------------------------------------
+template <int D, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_score_nn(ScoreArgs a)
 {
     using C = NetCfg<D>;
     constexpr int T = D * (D + 1) / 2;
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     for (int i = threadIdx.x; i < C::BLOB; i += WARPS * 32) smem[i] = __ldg(a.wfrag + i);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* stage = smem + C::BLOB + warp * (32 * C::STRIDE + 32);
     double* ystage = stage + 32 * C::STRIDE;
-    // zero the padding columns of this lane's staging row once
 #pragma unroll
     for (int k = C::NIN; k < C::STRIDE; ++k) stage[lane * C::STRIDE + k] = 0.0;
 
@@ -253,7 +235,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_score_full(ScoreArgs a)
         const i64 i = g * 32 + lane;
         const bool valid = i < a.N;
         if (!all_mode) load_list_indices<D>(a.idx, i, valid, c);
-        double lam = 0.0, dotq, max_elem;
+        double dotq, max_elem;
         {
             double xs[D], Xs[T], Qs[T];
             gather_point<D>(a, c, xs, Xs);
@@ -270,10 +252,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_score_full(ScoreArgs a)
             // max_elem = len * |max|, 1 if 0; Q~ = Q / max_elem   (cut_select_qp.py:536-538)
             max_elem = (double)D * mx;
             if (max_elem == 0.0) max_elem = 1.0;
+            const bool tiny = max_elem < 1e-280;   // subnormal-range coefficients: take the IEEE division
+            const double rme = fast_rcp(tiny ? 1.0 : max_elem);
             double s = 0.0;  // sum(map(mul, Q_slice, X_slice)) left to right, no FMA (cut_select_qp.py:575)
 #pragma unroll
             for (int q = 0; q < T; ++q) {
-                Qs[q] = __ddiv_rn(Qs[q], max_elem);
+                Qs[q] = tiny ? __ddiv_rn(Qs[q], max_elem) : div_by(Qs[q], max_elem, rme);
                 s = __dadd_rn(s, __dmul_rn(Qs[q], Xs[q]));
             }
             dotq = s;
@@ -285,26 +269,19 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_score_full(ScoreArgs a)
 #pragma unroll
             for (int q = 0; q < T; ++q)
                 row[D + q] = __dadd_rn(__dmul_rn(__dsub_rn(Qs[q], xoff[D + q]), gain[D + q]), -1.0);
-            if (WANT_LAM) lam = lam_min_subset<D>(xs, Xs, a.sweeps);
         }
         __syncwarp();
 #pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-            double y[2];
-            mlp16<D>(smem, stage, pass, lane, y);
-            if ((lane & 3) == 0) {
-                ystage[16 * pass + (lane >> 2)] = y[0];
-                ystage[16 * pass + 8 + (lane >> 2)] = y[1];
-            }
+        for (int pass = 0; pass < 4; ++pass) {
+            double y = mlp8<D>(smem, stage + 8 * pass * C::STRIDE, lane);
+            if ((lane & 3) == 0) ystage[8 * pass + (lane >> 2)] = y;
         }
         __syncwarp();
         if (valid) {
             double nn = ystage[lane];
             // obj = -sum * max_elem + NN * max_elem   (cut_select_qp.py:575, 582)
             double obj = __dadd_rn(__dmul_rn(-dotq, max_elem), __dmul_rn(nn, max_elem));
-            i64 o = a.pos ? __ldg(a.pos + i) : i;
-            a.obj[o] = obj;
-            if (WANT_LAM) a.lam[o] = lam;
+            a.obj[a.pos ? __ldg(a.pos + i) : i] = obj;
         }
         __syncwarp();
         if (all_mode && g + 1 < g1) {
@@ -321,7 +298,7 @@ template <int D, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_nn_eval(const double* wfrag, const double* in, i64 m, double* out)
 {
     using C = NetCfg<D>;
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     for (int i = threadIdx.x; i < C::BLOB; i += WARPS * 32) smem[i] = __ldg(wfrag + i);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -343,13 +320,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_nn_eval(const double* wfrag, 
         }
         __syncwarp();
 #pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-            double y[2];
-            mlp16<D>(smem, stage, pass, lane, y);
-            if ((lane & 3) == 0) {
-                ystage[16 * pass + (lane >> 2)] = y[0];
-                ystage[16 * pass + 8 + (lane >> 2)] = y[1];
-            }
+        for (int pass = 0; pass < 4; ++pass) {
+            double y = mlp8<D>(smem, stage + 8 * pass * C::STRIDE, lane);
+            if ((lane & 3) == 0) ystage[8 * pass + (lane >> 2)] = y;
         }
         __syncwarp();
         if (valid) out[i] = ystage[lane];
