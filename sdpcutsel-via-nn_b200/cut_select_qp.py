@@ -1,0 +1,308 @@
+"""Drop-in for the selection hot path of the reference's ``cut_select_qp.CutSolver``.
+
+Same method names, argument meaning, return formats and error behaviour as the reference for
+    _load_neural_nets              (cut_select_qp.py:284-303)
+    _get_sdp_vertex_cover          (cut_select_qp.py:377-541)
+    _sel_eigcut_by_ordering_on_measure (cut_select_qp.py:543-703, strat 1, 2, 4)
+    _gen_eigcuts_selected          (cut_select_qp.py:705-755)
+    _get_eigendecomp               (cut_select_qp.py:788-797)
+    __preprocess_triangle_ineq / __separate_and_add_triangle (cut_select_qp.py:799-863)
+but every score, selection and cut is computed by libsdpcutsel on the GPU.  The CPLEX LP loop
+(cut_select_algo), the instance readers and McCormick rows stay the reference's: mix this class in front of it
+ -- ``class CutSolver(B200CutSelection, reference.CutSolver)`` -- or use it standalone through
+``set_instance`` when no LP solver is around (tests, benchmarks).
+
+Narrowing: the ranked list a selection returns is only ever consumed as a prefix of length
+<= sel_size <= _SDP_CUTS_PER_ROUND_MAX, so strat 1 / 2 return the first ``_RANK_PREFIX`` (= 5000, or sel_size if
+larger) entries of the reference's list instead of all N; ``RankList.n_total`` / ``n_violated`` keep the counts.
+Out of scope and raising NotImplementedError: strat 3 / -1 (Mosek exact SDP), strat 5 (random shuffle),
+ch_ext 1 / 2 (chompack chordal extension).
+"""
+import numpy as np
+
+from . import _capi, cover, nn_weights
+
+try:  # the cut sink type of the reference (cut_select_qp.py:747); a plain container when CPLEX is absent
+    from cplex import SparsePair
+except ImportError:  # pragma: no cover - depends on the environment
+    class SparsePair(object):
+        def __init__(self, ind=None, val=None):
+            self.ind, self.val = list(ind), list(val)
+
+
+class RankList(list):
+    """Prefix of the reference's sorted rank_list plus the totals the full list would have had."""
+    n_total = 0
+    n_violated = 0
+
+
+class _RowSink(object):
+    """Stand-in for ``my_prob.linear_constraints`` when no CPLEX model is attached (collects the rows)."""
+
+    def __init__(self):
+        self.rows = []
+
+    def add(self, lin_expr=None, rhs=None, senses=None, **kw):
+        self.rows.extend(zip(lin_expr, rhs, senses))
+
+
+class _Prob(object):
+    def __init__(self):
+        self.linear_constraints = _RowSink()
+
+
+class B200CutSelection(object):
+    # class constants of the reference (cut_select_qp.py:22-41)
+    _THRES_MIN_OPT = 0
+    _THRES_NEG_EIGVAL = -10 ** (-15)
+    _BIG_M = 1000
+    _CONVERGENCE_TOL = 10 ** (-3)
+    _THRES_TRI_DENSE = 2
+    _THRES_TRI_VIOL = 10 ** (-7)
+    # the reference stops at 4e6 sub-problems because agg_list would not fit in RAM (cut_select_qp.py:35, 117,
+    # 527); nothing is materialised here, so the wall is the index width of the kernels (C(250,5) < 2^44)
+    _THRES_MAX_SUBS = 2 ** 44
+    _SDP_CUTS_PER_ROUND_MAX = 5000
+    _TRI_CUTS_PER_ROUND_MIN = 5000
+    _TRI_CUTS_PER_ROUND_MAX = 10000
+    _RANK_PREFIX = 5000          # length of the ranked prefix returned when the caller gives no sel_size
+    _DEVICE = 0
+
+    def __init__(self, *a, **kw):
+        super(B200CutSelection, self).__init__(*a, **kw)
+        for name, val in (("_dim", 0), ("_nb_vars", 0), ("_nb_lifted", 0), ("_Q", []), ("_Q_adj", []), ("_Q_arr", []),
+                          ("_my_prob", None), ("_agg_list", []), ("_nns", None), ("_rank_list_tri", []), ("_idx_list_tri", [])):
+            if not hasattr(self, name):
+                setattr(self, name, val)
+        self._blobs = {}
+        self._last_vars_values = None
+        self._tri_engine = None
+
+    # -- standalone setup (what __parse_boxqp_into_cplex leaves behind, cut_select_qp.py:313-328) ------
+    def set_instance(self, Q_arr, Q_adj, nb_vars, dim=None, my_prob=None):
+        self._Q_arr = np.ascontiguousarray(Q_arr, dtype=np.float64)
+        self._Q_adj = Q_adj
+        self._nb_vars, self._nb_lifted = int(nb_vars), int(nb_vars) * (int(nb_vars) + 1) // 2
+        if dim is not None:
+            self._dim = dim
+        self._my_prob = my_prob if my_prob is not None else _Prob()
+        self._agg_list, self._tri_engine = [], None
+
+    # -- engines ---------------------------------------------------------------------------------------
+    def _new_engine(self):
+        eng = _capi.Engine(self._DEVICE)
+        eng.set_params(thres_min_opt=float(self._THRES_MIN_OPT), thres_neg_eigval=float(self._THRES_NEG_EIGVAL),
+                       big_m=float(self._BIG_M), thres_tri_viol=float(self._THRES_TRI_VIOL),
+                       thres_tri_dense=int(self._THRES_TRI_DENSE))
+        for d, blob in self._blobs.items():
+            eng.set_weights(d, blob)
+        eng.set_instance(self._nb_vars, np.asarray(self._Q_arr, dtype=np.float64))
+        return eng
+
+    def _engine_for(self, agg_list):
+        """The device context that holds `agg_list` as its cover (the caller may re-point self._agg_list)."""
+        if not isinstance(agg_list, cover.AggList):
+            raise TypeError("self._agg_list must come from _get_sdp_vertex_cover (an AggList)")
+        if agg_list._engine is None:
+            eng = self._new_engine()
+            if agg_list.is_all:
+                eng.set_cover_all(agg_list.dim)
+            else:
+                eng.set_cover_list(agg_list.dim, agg_list.idx, agg_list.offset)
+            agg_list._engine = eng
+        return agg_list._engine
+
+    # -- reference surface -----------------------------------------------------------------------------
+    def _load_neural_nets(self):
+        """NN_2D.._dimD weights from the packed .m constants (replaces the ctypes load of neural_nets/NNs.so).
+        self._nns keeps the reference's shape: a list of (callable, input_array) per dimension 2.._dim."""
+        self._nns = []
+        for d in range(2, self._dim + 1):
+            if d not in self._blobs:
+                self._blobs[d] = nn_weights.load_packed(d)
+            input_arr = np.zeros(d * (d + 3) // 2)
+            self._nns.append((_NNFunc(self, d), input_arr))
+
+    def _get_sdp_vertex_cover(self, dim, ch_ext=0):
+        if ch_ext in (1, 2):
+            raise NotImplementedError("chordal-extension covers (ch_ext 1, 2) need chompack and are out of scope")
+        n = self._nb_vars
+        self._agg_list = None
+        Q_arr = np.asarray(self._Q_arr, dtype=np.float64)
+        if ch_ext == -1:   # P^E+: all subsets (the reference implements dim 3 only, cut_select_qp.py:451-455)
+            agg = cover.AggList(n, dim, Q_arr, n_all=_capi.binom(n, dim))
+        else:
+            adj = _as_dense_adj(self._Q_adj, n)
+            if _is_complete(adj):      # dense pattern: P^E_dim is all subsets in lex order -> nothing to store
+                agg = cover.AggList(n, dim, Q_arr, n_all=_capi.binom(n, dim))
+            else:
+                agg = cover.AggList(n, dim, Q_arr, idx=cover.pattern_E(adj, dim))
+        if len(agg) >= self._THRES_MAX_SUBS:
+            return len(agg)
+        self._agg_list = agg
+        return len(agg)
+
+    def _sel_eigcut_by_ordering_on_measure(self, strat, vars_values, cut_round, sel_size=0):
+        if strat in (3, 5, -1):
+            raise NotImplementedError("strat %d (exact SDP via Mosek / random / figure 8) is outside the GPU hot path" % strat)
+        if strat not in (1, 2, 4):
+            raise ValueError("strat must be 1 (feasibility), 2 (optimality) or 4 (combined)")
+        agg = self._agg_list
+        eng = self._engine_for(agg)
+        N = len(agg)
+        sel_size = min(sel_size, N)                                   # cut_select_qp.py:550
+        vars_values = np.ascontiguousarray(vars_values, dtype=np.float64)
+        self._last_vars_values = vars_values
+        n, nb_lifted = self._nb_vars, self._nb_lifted
+        if strat == 4 and sel_size == 0:
+            # the reference divides by sel_size, swallows the ZeroDivisionError and falls through (cut_select_qp.py:628-632)
+            strat_eff, k = 2, min(N, self._RANK_PREFIX)
+        else:
+            strat_eff = strat
+            k = sel_size if strat == 4 else min(N, max(sel_size, self._RANK_PREFIX))
+        res = eng.select(strat_eff, vars_values, k)
+        out = RankList()
+        out.n_total = N
+        out.n_violated = int(res["counts"][1])
+        X_vals, x_vals = vars_values[:nb_lifted], vars_values[nb_lifted:]
+        sets = self._sets_of(agg, res["idx"])
+        if strat_eff == 1:
+            for s, sc in zip(sets, res["score"]):
+                out.append((s, float(sc), cover.xarr_inds(n, s), len(s)))      # cut_select_qp.py:649
+            return out
+        for i, s, sc in zip(res["idx"], sets, res["score"]):
+            xi = cover.xarr_inds(n, s)
+            out.append((int(i), float(sc), tuple(x_vals[s]), tuple(X_vals[xi])))  # cut_select_qp.py:599
+        if strat_eff == 4:
+            return (int(res["new_strat"]), out)                                    # cut_select_qp.py:629-630
+        return out
+
+    def _sets_of(self, agg, idx):
+        if len(idx) == 0:
+            return []
+        if agg.is_all:
+            return [[int(v) for v in r] for r in _capi.unrank(agg.n, agg.dim, np.asarray(idx) - agg.offset)]
+        return [[int(v) for v in agg.idx[i - agg.offset] if v >= 0] for i in idx]
+
+    def _gen_eigcuts_selected(self, strat, sel_size, rank_list, strong_only=False, vars_values=None):
+        opt_sel, feas_sel, rand_sel = (strat in [2, 3, 4, -1]), (strat == 1), (strat == 5)
+        if rand_sel:
+            raise NotImplementedError("random selection (strat 5) is outside the GPU hot path")
+        my_prob, nb_lifted = self._my_prob, self._nb_lifted
+        sel_size = min(sel_size, len(rank_list))                                   # cut_select_qp.py:713
+        if vars_values is None:
+            vars_values = self._last_vars_values                                   # opt entries carry their own point
+        sets = []
+        for ix in range(sel_size):
+            entry = rank_list[ix]
+            if opt_sel:
+                idx, diff = entry[0], entry[1]
+                if strong_only and diff <= 0:                                      # cut_select_qp.py:725-726
+                    break
+                sets.append(self._sets_of(self._agg_list, [idx])[0])
+            else:
+                sets.append(list(entry[0]))
+        coeffs_sdp, rhs_sdp, senses_sdp = [], [], []
+        if sets:
+            dim = max(self._dim, max(len(s) for s in sets))
+            packed = np.full((len(sets), dim), -1, dtype=np.int16)
+            for i, s in enumerate(sets):
+                packed[i, :len(s)] = s
+            eng = self._engine_for(self._agg_list) if isinstance(self._agg_list, cover.AggList) else self._new_engine()
+            ind, val, rhs, lam, viol = eng.gen_cuts(dim, packed, vars_values)
+            for i, s in enumerate(sets):
+                if viol[i]:                                                        # eigvals[0] < _THRES_NEG_EIGVAL
+                    w = len(s) + len(s) * (len(s) + 1) // 2
+                    coeffs_sdp.append(SparsePair(ind=[int(v) for v in ind[i, :w]], val=[float(v) for v in val[i, :w]]))
+                    rhs_sdp.append(float(rhs[i]))
+                    senses_sdp.append("G")
+        my_prob.linear_constraints.add(lin_expr=coeffs_sdp, rhs=rhs_sdp, senses=senses_sdp)
+        return len(rhs_sdp)
+
+    def _get_eigendecomp(self, dim_subpr, curr_pt, X_slice, ev_yes):
+        eng = self._engine_for(self._agg_list) if isinstance(self._agg_list, cover.AggList) else self._new_engine()
+        vals, vecs = eng.eigendecomp(dim_subpr, curr_pt, X_slice, want_vecs=bool(ev_yes))
+        return (vals, vecs) if ev_yes else vals
+
+    # name-mangled exactly like the reference's private triangle methods (_CutSolver__...)
+    def _tri_preprocess(self):
+        n = self._nb_vars
+        eng = self._new_engine()
+        eng.set_tri_pattern(_as_dense_adj(self._Q_adj, n))
+        self._tri_engine = eng
+        self._rank_list_tri, self._idx_list_tri = None, None     # the per-triple lists are not materialised
+
+    def _tri_separate(self, sel_size, vars_values):
+        if self._tri_engine is None:
+            self._tri_preprocess()
+        n, nb_lifted, my_prob = self._nb_vars, self._nb_lifted, self._my_prob
+        t = self._tri_engine.triangles(vars_values, self._TRI_CUTS_PER_ROUND_MAX)
+        V = t["n_violated"]
+        nb_tri_cuts = max(min(self._TRI_CUTS_PER_ROUND_MIN, int(np.floor(sel_size * V))),
+                          min(self._TRI_CUTS_PER_ROUND_MAX, V))                    # cut_select_qp.py:843-844
+        if nb_tri_cuts > V:
+            raise IndexError("list index out of range")                            # the reference indexes past the list here
+        triples = _capi.unrank(n, 3, t["rank"][:nb_tri_cuts]) if nb_tri_cuts else np.zeros((0, 3), np.int32)
+        dict_coeffs_tri = {0: [-1, -1, 1, 1], 1: [-1, 1, -1, 1], 2: [1, -1, -1, 1], 3: [1, 1, 1, -1, -1, -1]}
+        coeffs_tri, rhs_tri, senses_tri = [0] * nb_tri_cuts, [0] * nb_tri_cuts, ["G"] * nb_tri_cuts
+        for ix in range(nb_tri_cuts):
+            i1, i2, i3 = (int(v) for v in triples[ix])
+            typ = int(t["type"][ix])
+            x12, x13, x23 = n * i1 - i1 * (i1 + 1) // 2 + i2, n * i1 - i1 * (i1 + 1) // 2 + i3, n * i2 - i2 * (i2 + 1) // 2 + i3
+            if typ == 3:
+                coeffs_tri[ix] = SparsePair(ind=[x12, x13, x23, i1 + nb_lifted, i2 + nb_lifted, i3 + nb_lifted], val=dict_coeffs_tri[3])
+                rhs_tri[ix] = -1
+            else:
+                coeffs_tri[ix] = SparsePair(ind=[x12, x13, x23, (i1, i2, i3)[typ] + nb_lifted], val=dict_coeffs_tri[typ])
+                rhs_tri[ix] = 0
+        my_prob.linear_constraints.add(lin_expr=coeffs_tri, rhs=rhs_tri, senses=senses_tri)
+        return nb_tri_cuts
+
+
+class _NNFunc(object):
+    """Callable with the signature of NNs.so's neural_net_dD (cut_select_qp.py:579-582), evaluated on the GPU."""
+
+    def __init__(self, owner, d):
+        self.owner, self.d, self.eng = owner, d, None
+        self.restype = None
+
+    def __call__(self, input_arr):
+        if self.eng is None:
+            self.eng = _capi.Engine(self.owner._DEVICE)
+            self.eng.set_weights(self.d, self.owner._blobs[self.d])
+        return float(self.eng.nn_eval(self.d, np.asarray(list(input_arr), dtype=np.float64))[0])
+
+
+def _as_dense_adj(Q_adj, n):
+    """numpy 0/1 pattern from a numpy array or a cvxopt spmatrix (cut_select_qp.py:323-326)."""
+    if isinstance(Q_adj, np.ndarray):
+        return (Q_adj != 0).astype(np.uint8)
+    A = np.zeros((n, n), dtype=np.uint8)
+    try:
+        for i, j in zip(Q_adj.I, Q_adj.J):       # cvxopt.spmatrix
+            A[int(i), int(j)] = 1
+    except AttributeError:
+        for i in range(n):
+            for j in range(n):
+                A[i, j] = 1 if Q_adj[i, j] else 0
+    return A
+
+
+def _is_complete(adj):
+    n = adj.shape[0]
+    off = (adj | adj.T).astype(bool)
+    off[np.arange(n), np.arange(n)] = True
+    return bool(off.all())
+
+
+class CutSolver(B200CutSelection):
+    """Standalone solver object exposing the reference's hot-path surface (no LP loop)."""
+
+    def __init__(self):
+        super(CutSolver, self).__init__()
+
+    def __preprocess_triangle_ineq(self):          # -> _CutSolver__preprocess_triangle_ineq
+        return self._tri_preprocess()
+
+    def __separate_and_add_triangle(self, sel_size, vars_values):   # -> _CutSolver__separate_and_add_triangle
+        return self._tri_separate(sel_size, vars_values)

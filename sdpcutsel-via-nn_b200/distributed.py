@@ -34,9 +34,9 @@ class ShardedSelector(object):
         t = torch.from_numpy(np.ascontiguousarray(arr))
         if self.device is not None:
             t = t.to(self.device)
-        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
         self.dist.all_gather_into_tensor(out, t, group=self.group)
-        return out.cpu().numpy()
+        return out.cpu().numpy().reshape((self.world,) + tuple(t.shape))
 
     def _allreduce_sum(self, arr):
         if self.world == 1:

@@ -1,0 +1,68 @@
+"""CPU tests of the host-side logic of the product (no GPU): vertex-cover construction, the lazy agg_list,
+synthetic inputs, weight blobs."""
+import numpy as np
+import pytest
+
+import sdpcutsel_via_nn_b200 as pkg
+from conftest import inst_arrays
+from oracle import cutsel_oracle as orc
+
+
+@pytest.mark.parametrize("name", ["spar030-060-1", "spar040-030-1", "spar050-030-1"])
+@pytest.mark.parametrize("dim", [3, 4, 5])
+def test_pattern_E_cover_matches_reference(golden, name, dim):
+    n, Q_arr, adj = inst_arrays(golden, name)
+    idx = pkg.cover.pattern_E(adj, dim)
+    assert np.array_equal(idx, golden["cover_%s_d%d" % (name.replace("-", "_"), dim)])
+
+
+def test_pattern_E_spar125(golden):
+    n, Q_arr, adj = inst_arrays(golden, "spar125-075-1")
+    idx = pkg.cover.pattern_E(adj, 3)
+    assert idx.shape[0] == 133242                                   # data_tables nb_subproblems
+    assert np.array_equal(idx, orc.cover_pattern_E(adj, 3)[0])
+
+
+def test_agg_list_elements(golden):
+    n, Q_arr, adj = inst_arrays(golden, "spar030-060-1")
+    for dim in (3, 4, 5):
+        agg = pkg.cover.AggList(n, dim, Q_arr, idx=pkg.cover.pattern_E(adj, dim))
+        Qs = golden["agg_spar030_060_1_d%d_Qslice" % dim]
+        me = golden["agg_spar030_060_1_d%d_maxelem" % dim]
+        assert len(agg) == Qs.shape[0]
+        for i in (0, 1, len(agg) // 2, len(agg) - 1):
+            s, xi, q, m = agg[i]
+            assert xi == orc.xarr_inds(n, s) and m == me[i]
+            assert np.array_equal(np.array(q), Qs[i, :len(q)])
+        assert agg[:] is agg and len(agg[2:5]) == 3
+    allc = pkg.cover.AggList(n, 3, Q_arr, n_all=4060)
+    assert len(allc) == 4060 and allc[4059][0] == [27, 28, 29] and allc[0][0] == [0, 1, 2]
+
+
+def test_synthetic_inputs_match_oracle_recipe():
+    Qf = pkg.synthetic.instance(40, 0.75, seed=7)
+    assert np.array_equal(Qf, orc.synth_instance(40, 0.75, seed=7)) and np.array_equal(Qf, Qf.T)
+    a, b = pkg.synthetic.boxqp_arrays(Qf), orc.boxqp_arrays(Qf)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert np.array_equal(pkg.synthetic.lp_point(40, 8), orc.synth_point(40, 8))
+
+
+@pytest.mark.parametrize("d", [2, 3, 4, 5])
+def test_weight_blob_roundtrip(blobs, d):
+    net = pkg.nn_weights.unpack_blob(blobs[d])
+    assert np.array_equal(pkg.nn_weights.pack_blob(net), blobs[d])
+    nin, h = d * (d + 3) // 2, (64 if d in (2, 5) else 50)
+    assert net["W"][0].shape == (h, nin) and net["W"][-1].shape == (1, h) and len(net["W"]) == (5 if d == 5 else 4)
+
+
+def test_solver_surface_names():
+    cs = pkg.CutSolver()
+    for name in ("_load_neural_nets", "_get_sdp_vertex_cover", "_sel_eigcut_by_ordering_on_measure", "_gen_eigcuts_selected",
+                 "_get_eigendecomp", "_CutSolver__preprocess_triangle_ineq", "_CutSolver__separate_and_add_triangle"):
+        assert callable(getattr(cs, name))
+    assert hasattr(pkg.CutSolverQCQP(), "_CutSolverQCQP__get_vertex_cover")
+    assert (cs._THRES_NEG_EIGVAL, cs._BIG_M, cs._SDP_CUTS_PER_ROUND_MAX, cs._TRI_CUTS_PER_ROUND_MAX) == (-1e-15, 1000, 5000, 10000)
+    with pytest.raises(NotImplementedError):
+        cs._sel_eigcut_by_ordering_on_measure(3, None, 1)
+    with pytest.raises(NotImplementedError):
+        cs._get_sdp_vertex_cover(3, ch_ext=1)
