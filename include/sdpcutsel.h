@@ -44,7 +44,8 @@ typedef struct sdpcs_params {
     double big_m;            /* _BIG_M            = 1000   */
     double thres_tri_viol;   /* _THRES_TRI_VIOL   = 1e-7   */
     int32_t thres_tri_dense; /* _THRES_TRI_DENSE  = 2      */
-    int32_t jacobi_sweeps;   /* 0 = built-in default per matrix order */
+    int32_t jacobi_sweeps;   /* scoring: 0 = Householder tridiagonalisation + Laguerre (default), > 0 = cyclic
+                              * Jacobi with that many sweeps; cut generation always uses Jacobi (needs vectors) */
 } sdpcs_params;
 
 /* Device timings (ms, CUDA events on the context's stream) of the last sdpcs_score / sdpcs_topk calls. */

@@ -433,7 +433,7 @@ static int launch_score(sdpcs_ctx* ctx, int want, const uint8_t* idx, const i64*
     a.n = ctx->n; a.N = N; a.rank_begin = rank_begin; a.idx = idx; a.pos = pos;
     a.X = ctx->d_vars; a.x = ctx->d_vars + (size_t)ctx->n * (ctx->n + 1) / 2; a.Q = ctx->d_Q;
     a.wfrag = ctx->d_wfrag[D]; a.lam = ctx->d_lam; a.obj = ctx->d_obj;
-    a.sweeps = ctx->params.jacobi_sweeps > 0 ? ctx->params.jacobi_sweeps : default_sweeps(D + 1);
+    a.sweeps = ctx->params.jacobi_sweeps > 0 ? ctx->params.jacobi_sweeps : 0;   // 0: tridiagonalisation + Laguerre
     const i64 groups = (N + 31) / 32;
     if (want & 1) {   // K1+K2+K3: lam_min of every candidate
         int occ = 0;

@@ -256,3 +256,24 @@ def test_errors_are_loud(capi, blobs):
     assert eng.num_candidates == 0
     r = eng.select(1, np.zeros(65), 10)
     assert r["idx"].size == 0
+
+
+@pytest.mark.parametrize("rho", [2, 3, 4, 5])
+def test_eigen_methods_vs_lapack(capi, blobs, golden, rho):
+    """Default eigen path (Householder tridiagonalisation + Laguerre) and the Jacobi path (jacobi_sweeps > 0)
+    against numpy/LAPACK eigvalsh on random and on degenerate (x = 0.5, X in {0, 0.5}) LP points."""
+    n = 26
+    Q_arr, adj = orc.boxqp_arrays(orc.synth_instance(n, 0.6, seed=11))
+    idx = orc.cover_all(n, rho)
+    sizes = np.full(idx.shape[0], rho)
+    for vv in (orc.synth_point(n, seed=3), orc.degenerate_point(n, Q_arr), np.zeros(n * (n + 1) // 2 + n),
+               np.ones(n * (n + 1) // 2 + n)):
+        lam_o, _ = orc.score_cover(Q_arr, n, idx, sizes, vv, want_obj=False)
+        for sweeps in (0, 6):
+            eng = capi.Engine(0)
+            eng.set_params(jacobi_sweeps=sweeps)
+            eng.set_instance(n, Q_arr)
+            eng.set_cover_all(rho)
+            eng.score(vv, 1)
+            lam, _ = eng.scores(obj=False)
+            assert np.abs(lam - lam_o).max() < 2e-14, (rho, sweeps)
