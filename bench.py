@@ -135,6 +135,8 @@ def main():
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--strat", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nn-engine", default="tcgen05", choices=["tcgen05", "dmma"],
+                    help="NN_rhoD evaluation: int8-sliced tcgen05 contraction (default) or FP64 DMMA")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -164,6 +166,7 @@ def main():
     with torch.cuda.stream(stream):
         eng = pkg._capi.Engine(local_rank)
         eng.set_stream(stream.cuda_stream)
+        eng.set_params(nn_engine=pkg._capi.NN_DMMA if args.nn_engine == "dmma" else pkg._capi.NN_TCGEN05)
         eng.set_weights(rho, pkg.nn_weights.load_packed(rho))
         eng.set_instance(n, Q_arr)
         eng.set_cover_all(rho, r0, r1)
@@ -185,14 +188,14 @@ def main():
             time.sleep(0.3)
         # ---- device-resident timed region ---------------------------------------------------------
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        score_ms, select_ms, launches = 0.0, 0.0, 0
+        score_ms, select_ms, nn_ms, launches, fallbacks = 0.0, 0.0, 0.0, 0, 0
         barrier()
         t_wall0 = time.time()
         e0.record(stream)
         for _ in range(args.steps):
             res = sel.select(args.strat, None, k)
             tm = eng.timings()
-            score_ms += tm["score_ms"]; select_ms += tm["select_ms"]
+            score_ms += tm["score_ms"]; select_ms += tm["select_ms"]; nn_ms += tm["nn_ms"]; fallbacks = tm["nn_fallbacks"]
             launches += tm["score_launches"] + tm["select_launches"] * (2 if args.strat == 4 else 1)
         e1.record(stream)
         barrier()
@@ -208,22 +211,52 @@ def main():
         barrier()
         ms_e2e = e2.elapsed_time(e3)
         clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-        t = torch.tensor([ms_dev, ms_e2e, score_ms / args.steps], dtype=torch.float64, device=dev)
+        # cross-check at full size (not timed): the FP64 DMMA engine must select the identical list
+        engines_agree = None
+        if args.nn_engine == "tcgen05":
+            eng.set_params(nn_engine=pkg._capi.NN_DMMA)
+            res_dmma = sel.select(args.strat, None, k)
+            eng.set_params(nn_engine=pkg._capi.NN_TCGEN05)
+            engines_agree = bool(np.array_equal(res["idx"], res_dmma["idx"]))
+        t = torch.tensor([ms_dev, ms_e2e, score_ms / args.steps, nn_ms / args.steps, select_ms / args.steps], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_dev, ms_e2e, score_ms_step = (float(v) for v in t.cpu())
+        ms_dev, ms_e2e, score_ms_step, nn_ms_step, select_ms_step = (float(v) for v in t.cpu())
 
     if rank == 0:
         W = W_FLOPS[rho]
         n_local = r1 - r0
         achieved = n_local * W / (score_ms_step * 1e-3) * 1e-12
         traffic = None
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        bf16 = json.load(open(peaks_path)).get("bf16_tflops_sustained") if os.path.exists(peaks_path) else None
+        bf16_src = "2 x bf16_tflops_sustained of MEASURED_PEAKS.json" if bf16 else "2 x 1400 (B200_PROFILING.md fallback)"
+        bf16 = bf16 or 1400.0
         prof = os.path.join(ROOT, "profiles", "ncu_summary.json")
         if os.path.exists(prof):
             try:
                 traffic = json.load(open(prof)).get("score_kernel_dram_bytes_per_launch")
             except Exception:
                 traffic = None
+        if args.nn_engine == "tcgen05":
+            # int8 tensor operations actually issued per candidate: 28 digit pairs x (32 + (NHID-1) x 64) x 64 MACs x 2
+            nhid = 4 if rho == 5 else 3
+            i8_ops = 28 * (32 + (nhid - 1) * 64) * 64 * 2
+            i8_tops = n_local * i8_ops / (nn_ms_step * 1e-3) * 1e-12
+            kname = "k_mlp_i8<%d> (tcgen05.mma kind::i8, error-free 7x7-digit slicing of the FP64 MLP, TMEM accumulators) " \
+                    "+ k_prep_i8<%d> + k_score_feas<%d> (FP64 tridiagonal + Laguerre)" % (nhid, rho, rho)
+            extra = dict(nn_kernels_ms=nn_ms_step, int8_tensor=dict(achieved=i8_tops, peak=2 * bf16, unit="TOP/s", frac=i8_tops / (2 * bf16),
+                                                                  ops_per_subset=i8_ops, peak_source=bf16_src),
+                         note="achieved/peak are FP64-equivalent: algorithmic FP64 flop of SURVEY 8(d) over the measured FP64 DMMA peak "
+                              "(north_star's FP64 roofline); the contraction itself runs on the int8 tensor pipe, see int8_tensor")
+        else:
+            kname = "k_score_nn<%d,16> (DMMA.8x8x4 FP64 MLP) + k_score_feas<%d> (FP64 tridiagonal + Laguerre)" % (rho, rho)
+            extra = dict(nn_kernels_ms=nn_ms_step)
+        roofline = dict(bound="tensor", kernel=kname, achieved=achieved, peak=peak["dmma_tflops"], unit="TFLOP/s",
+                        frac=achieved / peak["dmma_tflops"], traffic=traffic, flops_per_subset=W, subsets_per_launch=n_local,
+                        kernel_ms=score_ms_step, select_ms=select_ms_step, nn_engine=args.nn_engine, nn_fallbacks=int(fallbacks),
+                        peak_source="FP64 DMMA.8x8x4 micro-benchmark run in this process (MEASURED_PEAKS.json has no FP64 entry); DFMA peak %.1f" % peak["dfma_tflops"],
+                        **extra)
         out = dict(
             metric="candidate cuts scored+selected/sec", value=N * args.steps / (ms_dev * 1e-3), unit="subsets/s",
             n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_dev / args.steps, higher_is_better=True,
@@ -233,13 +266,11 @@ def main():
             e2e=dict(value=N * args.steps / (ms_e2e * 1e-3), unit="subsets/s", ms_per_step=ms_e2e / args.steps,
                      h2d_bytes_per_step=int(vv.size * 8), d2h_bytes_per_step=int((2 if args.strat == 4 else 1) * (k * 32 + 8288))),
             gpu_launches=int(launches),
-            roofline=dict(bound="tensor", kernel="k_score_nn<%d,16> (DMMA.8x8x4 FP64 MLP) + k_score_feas<%d> (FP64 Jacobi)" % (rho, rho), achieved=achieved,
-                          peak=peak["dmma_tflops"], unit="TFLOP/s", frac=achieved / peak["dmma_tflops"], traffic=traffic,
-                          flops_per_subset=W, subsets_per_launch=n_local, kernel_ms=score_ms_step,
-                          peak_source="FP64 DMMA.8x8x4 micro-benchmark run in this process (MEASURED_PEAKS.json has no FP64 entry); DFMA peak %.1f" % peak["dfma_tflops"]),
+            roofline=roofline,
             clocks=clocks,
             selection=dict(n_selected=int(res["idx"].size), new_strat=int(res["new_strat"]), counts=[int(v) for v in res["counts"]],
-                           e2e_matches_resident=bool(np.array_equal(res["idx"], res_e2e["idx"]))),
+                           e2e_matches_resident=bool(np.array_equal(res["idx"], res_e2e["idx"])),
+                           tcgen05_and_dmma_engines_select_identically=engines_agree),
         )
         if world == 1 and not args.no_cpu_baseline:
             sample_n = min(N, 1000000)

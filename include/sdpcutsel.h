@@ -46,7 +46,18 @@ typedef struct sdpcs_params {
     int32_t thres_tri_dense; /* _THRES_TRI_DENSE  = 2      */
     int32_t jacobi_sweeps;   /* scoring: 0 = Householder tridiagonalisation + Laguerre (default), > 0 = cyclic
                               * Jacobi with that many sweeps; cut generation always uses Jacobi (needs vectors) */
+    int32_t nn_engine;       /* NN_rhoD evaluation: SDPCS_NN_TCGEN05 (default) or SDPCS_NN_DMMA */
+    int32_t reserved;        /* 0 */
 } sdpcs_params;
+
+/* NN engines.  Both evaluate neural_net_{2..5}D (cut_select_qp.py:579-582) to FP64 accuracy:
+ *   TCGEN05: error-free int8-sliced contraction on the 5th-generation tensor cores (tcgen05.mma kind::i8,
+ *            accumulators in TMEM), FP64 only for bias / tansig; NN inputs must lie in (-2, 2) after mapminmax
+ *            (always true for LP points in the McCormick box) -- otherwise the call transparently re-scores
+ *            with the DMMA engine and counts it in sdpcs_timings.nn_fallbacks;
+ *   DMMA:    FP64 tensor-core contraction (mma.sync.m8n8k4.f64). */
+#define SDPCS_NN_TCGEN05 0
+#define SDPCS_NN_DMMA 1
 
 /* Device timings (ms, CUDA events on the context's stream) of the last sdpcs_score / sdpcs_topk calls. */
 typedef struct sdpcs_timings {
@@ -55,6 +66,8 @@ typedef struct sdpcs_timings {
     double h2d_ms;        /* upload of vars_values                                      */
     int64_t score_launches;
     int64_t select_launches;
+    int64_t nn_fallbacks; /* sdpcs_score calls that re-scored with the DMMA engine (input range), cumulative */
+    double nn_ms;         /* the NN part of score_ms (K1+K2+K4 launches), 0 if the last score had no NN part */
 } sdpcs_timings;
 
 int sdpcs_default_params(sdpcs_params *p);
@@ -150,6 +163,10 @@ int sdpcs_triangles(sdpcs_ctx *ctx, const double *vars_values, int64_t kmax, int
 /* Batched NN_rhoD forward pass on the GPU for m input rows of length rho(rho+3)/2 -- the replacement of
  * `neural_net_%dD(input_arr)` (cut_select_qp.py:579-582). */
 int sdpcs_nn_eval(sdpcs_ctx *ctx, int rho, const double *inputs, int64_t m, double *out);
+
+/* Test hook for the TCGEN05 engine: the scaled pre-activations z = -2 log2(e) (W a + b) of tansig layer
+ * `layer` (0-based) for m input rows, out_z is m x 64 (neurons beyond the layer width are zero padded). */
+int sdpcs_nn_debug_layer(sdpcs_ctx *ctx, int rho, const double *inputs, int64_t m, int layer, double *out_z);
 
 /* FP64 roofline denominators measured on this device: DFMA and DMMA.8x8x4 peak TFLOP/s. */
 int sdpcs_fp64_peak(sdpcs_ctx *ctx, double *dfma_tflops, double *dmma_tflops);

@@ -19,18 +19,21 @@ EXPORTS = [
     "sdpcs_get_timings", "sdpcs_set_weights", "sdpcs_set_instance", "sdpcs_set_cover_all", "sdpcs_set_cover_list",
     "sdpcs_num_candidates", "sdpcs_score", "sdpcs_scores", "sdpcs_counts", "sdpcs_topk", "sdpcs_merge_topk",
     "sdpcs_select", "sdpcs_unrank", "sdpcs_binom", "sdpcs_gen_cuts", "sdpcs_eigendecomp", "sdpcs_set_tri_pattern",
-    "sdpcs_triangles", "sdpcs_nn_eval", "sdpcs_fp64_peak",
+    "sdpcs_triangles", "sdpcs_nn_eval", "sdpcs_nn_debug_layer", "sdpcs_fp64_peak",
 ]
+
+NN_TCGEN05, NN_DMMA = 0, 1
 
 
 class Params(ctypes.Structure):
     _fields_ = [("thres_min_opt", c_dbl), ("thres_neg_eigval", c_dbl), ("big_m", c_dbl), ("thres_tri_viol", c_dbl),
-                ("thres_tri_dense", ctypes.c_int32), ("jacobi_sweeps", ctypes.c_int32)]
+                ("thres_tri_dense", ctypes.c_int32), ("jacobi_sweeps", ctypes.c_int32), ("nn_engine", ctypes.c_int32),
+                ("reserved", ctypes.c_int32)]
 
 
 class Timings(ctypes.Structure):
     _fields_ = [("score_ms", c_dbl), ("select_ms", c_dbl), ("h2d_ms", c_dbl), ("score_launches", c_i64),
-                ("select_launches", c_i64)]
+                ("select_launches", c_i64), ("nn_fallbacks", c_i64), ("nn_ms", c_dbl)]
 
 
 _lib = None
@@ -196,7 +199,7 @@ class Engine(object):
         t = Timings()
         self._ck(self._lib.sdpcs_get_timings(self._ctx, ctypes.byref(t)))
         return dict(score_ms=t.score_ms, select_ms=t.select_ms, h2d_ms=t.h2d_ms, score_launches=t.score_launches,
-                    select_launches=t.select_launches)
+                    select_launches=t.select_launches, nn_fallbacks=t.nn_fallbacks, nn_ms=t.nn_ms)
 
     # -- cuts / eig / triangles / nn ---------------------------------------------------------------
     def gen_cuts(self, rho, sets, vars_values):
@@ -235,6 +238,13 @@ class Engine(object):
         x = _f64(inputs).reshape(-1, rho * (rho + 3) // 2)
         out = np.empty(x.shape[0])
         self._ck(self._lib.sdpcs_nn_eval(self._ctx, c_int(rho), _ptr(x), c_i64(x.shape[0]), _ptr(out)))
+        return out
+
+    def nn_debug_layer(self, rho, inputs, layer):
+        """Test hook: scaled pre-activations of tansig layer `layer` from the tcgen05 engine, (m, 64)."""
+        x = _f64(inputs).reshape(-1, rho * (rho + 3) // 2)
+        out = np.empty((x.shape[0], 64))
+        self._ck(self._lib.sdpcs_nn_debug_layer(self._ctx, c_int(rho), _ptr(x), c_i64(x.shape[0]), c_int(layer), _ptr(out)))
         return out
 
     def fp64_peak(self):

@@ -10,6 +10,7 @@
 #include "../../include/sdpcutsel.h"
 #include "aux_kernels.cuh"
 #include "score_kernels.cuh"
+#include "mlp_i8_kernels.cuh"
 #include "select_kernels.cuh"
 
 using namespace sdpcs;
@@ -29,6 +30,13 @@ struct sdpcs_ctx {
     double* h_vars = nullptr;      // pinned staging
     // weights (fragment-ordered), index = rho
     double* d_wfrag[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // weights as int8 digit images + FP64 parameter block for the tcgen05 MLP (mlp_i8_kernels.cuh)
+    uint8_t* d_wi8[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint8_t* d_tiles = nullptr;    // layer-0 digit images of one chunk of candidates
+    i64 tiles_cap = 0;             // in bytes
+    int* d_status = nullptr;       // device status word of the tcgen05 pipeline
+    int* h_status = nullptr;       // pinned
+    bool i8_used = false;
     // cover
     int rho = 0, mode = 0;         // mode 0 none, 1 all-subsets, 2 list
     i64 N = 0, base = 0;           // base = agg_idx of local candidate 0 (rank_begin / agg_offset)
@@ -59,8 +67,8 @@ struct sdpcs_ctx {
     void* d_scratch = nullptr;
     size_t scratch_bytes = 0;
     // timing
-    cudaEvent_t ev[6];
-    bool ev_score = false, ev_select = false, ev_h2d = false;
+    cudaEvent_t ev[8];
+    bool ev_score = false, ev_select = false, ev_h2d = false, ev_nn = false;
     sdpcs_timings tm;
 
     int fail(int code, const std::string& m) { err = m; return code; }
@@ -162,6 +170,58 @@ static bool pack_fragments(const double* blob, i64 len, std::vector<double>& out
 }
 
 // ---------------------------------------------------------------------------------------------------
+// NN weights: blob -> int8 digit images (UMMA canonical K-major layout) + FP64 parameter block for k_mlp_i8.
+// Row j of a layer is scaled by 2^e >= max|W[j,:]|, rounded to 54 fractional bits and written as 7 balanced
+// base-256 digits (slice 0 = most significant).  oracle/nn_i8_model.py states the same arithmetic.
+// ---------------------------------------------------------------------------------------------------
+template <int D>
+static void pack_i8(const double* blob, std::vector<uint8_t>& out)
+{
+    using C = NetCfg<D>;
+    using L = I8Smem<C::NHID>;
+    const int n_in = C::NIN, h = C::H, NL = C::NHID + 1;
+    const double* xo = blob + 3;
+    const double* p = xo + 2 * n_in;
+    std::vector<const double*> W(NL), B(NL);
+    for (int l = 0; l < NL; ++l) {
+        int rows = (l == NL - 1) ? 1 : h, cols = (l == 0) ? n_in : h;
+        W[l] = p; p += (i64)rows * cols;
+        B[l] = p; p += rows;
+    }
+    const double y_gain = p[0], y_xoff = p[1];
+    out.assign(L::GLOBAL_BYTES, 0);
+    double* par = reinterpret_cast<double*>(out.data() + L::W_TOTAL);
+    for (int l = 0; l < C::NHID; ++l) {
+        const int cols = (l == 0) ? n_in : h, K = (l == 0) ? I8_K0 : 64;
+        const int ea = (l == 0) ? 53 : 54;              // digits carry 8 * rint(a * 2^50) resp. 8 * rint(a * 2^51)
+        uint8_t* img = out.data() + (l == 0 ? 0 : I8_W0_BYTES + (l - 1) * I8_WH_BYTES);
+        for (int j = 0; j < I8_N; ++j) {
+            double mx = 0.0;
+            if (j < h) for (int k = 0; k < cols; ++k) mx = std::max(mx, std::fabs(W[l][j * cols + k]));
+            int e = 0;
+            if (mx > 0.0) std::frexp(mx, &e);           // mx = f * 2^e, f in [0.5, 1): 2^e > = mx
+            for (int k = 0; k < K; ++k) {
+                const double w = (j < h && k < cols) ? W[l][j * cols + k] : 0.0;
+                const long long wint = std::llrint(std::ldexp(w, 54 - e));
+                const unsigned long long u = (unsigned long long)(wint + 0x0080808080808080ll);
+                for (int b = 0; b < I8_NS; ++b) {
+                    const int digit = (int)((u >> (8 * b)) & 0xFF) - 128;
+                    img[(6 - b) * (I8_N * K) + (k / 16) * (I8_N * 16) + j * 16 + (k % 16)] = (uint8_t)(int8_t)digit;
+                }
+            }
+            // z = -2 log2(e) * (W a + b);  W a = 2^(e - 54) * 2^-ea * 2^48 * (sum of the kept digit-pair diagonals)
+            par[L::P_CS + l * 64 + j] = std::ldexp(1.0, e - 54 - ea + 48) * SDPCS_TANSIG_SCALE;
+            par[L::P_BS + l * 64 + j] = (j < h) ? SDPCS_TANSIG_SCALE * B[l][j] : 0.0;
+        }
+    }
+    for (int j = 0; j < h; ++j) par[L::P_WOUT + j] = W[NL - 1][j];
+    par[L::P_MISC + 0] = B[NL - 1][0];
+    par[L::P_MISC + 1] = y_gain;
+    par[L::P_MISC + 2] = y_xoff;
+    for (int j = 0; j < 256; ++j) par[L::P_TAB + j] = (double)exp2l((long double)j / 256.0L);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // basic API
 // ---------------------------------------------------------------------------------------------------
 extern "C" int sdpcs_default_params(sdpcs_params* p)
@@ -173,6 +233,8 @@ extern "C" int sdpcs_default_params(sdpcs_params* p)
     p->thres_tri_viol = 1e-7;
     p->thres_tri_dense = 2;
     p->jacobi_sweeps = 0;
+    p->nn_engine = SDPCS_NN_TCGEN05;
+    p->reserved = 0;
     return SDPCS_OK;
 }
 
@@ -203,7 +265,9 @@ extern "C" int sdpcs_create(sdpcs_ctx** out, int device)
     memset(&ctx->tm, 0, sizeof(ctx->tm));
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMalloc(&ctx->d_state, sizeof(SelState)) != cudaSuccess ||
-        cudaMalloc(&ctx->d_tri_counters, 2 * sizeof(unsigned long long)) != cudaSuccess) {
+        cudaMalloc(&ctx->d_tri_counters, 2 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_status, sizeof(int)) != cudaSuccess || cudaMallocHost(&ctx->h_status, sizeof(int)) != cudaSuccess ||
+        cudaMemset(ctx->d_status, 0, sizeof(int)) != cudaSuccess) {
         g_create_error = "context allocation failed";
         delete ctx;
         return SDPCS_ERR_CUDA;
@@ -221,15 +285,17 @@ extern "C" int sdpcs_destroy(sdpcs_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     void* ptrs[] = {ctx->d_Q, ctx->d_vars, ctx->d_lam, ctx->d_obj, ctx->d_key1, ctx->d_key2, ctx->d_state, ctx->d_c_k1,
                     ctx->d_c_k2, ctx->d_s_k1, ctx->d_s_k2, ctx->d_c_idx, ctx->d_s_idx, ctx->d_s_perm, ctx->d_o_score,
-                    ctx->d_o_lam, ctx->d_o_obj, ctx->d_adj, ctx->d_tri_counters, ctx->d_scratch};
+                    ctx->d_o_lam, ctx->d_o_obj, ctx->d_adj, ctx->d_tri_counters, ctx->d_scratch, ctx->d_tiles, ctx->d_status};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int d = 0; d < 6; ++d) {
         if (ctx->d_wfrag[d]) cudaFree(ctx->d_wfrag[d]);
+        if (ctx->d_wi8[d]) cudaFree(ctx->d_wi8[d]);
         if (ctx->d_idx[d]) cudaFree(ctx->d_idx[d]);
         if (ctx->d_pos[d]) cudaFree(ctx->d_pos[d]);
     }
     if (ctx->h_vars) cudaFreeHost(ctx->h_vars);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
+    if (ctx->h_status) cudaFreeHost(ctx->h_status);
     for (auto& ev : ctx->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -259,6 +325,8 @@ extern "C" int sdpcs_get_timings(const sdpcs_ctx* cctx, sdpcs_timings* t)
     float ms;
     if (ctx->ev_h2d) { CU(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5])); ctx->tm.h2d_ms = ms; }
     if (ctx->ev_score) { CU(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1])); ctx->tm.score_ms = ms; }
+    ctx->tm.nn_ms = 0.0;
+    if (ctx->ev_score && ctx->ev_nn) { CU(cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7])); ctx->tm.nn_ms = ms; }
     if (ctx->ev_select) { CU(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3])); ctx->tm.select_ms = ms; }
     *t = ctx->tm;
     return SDPCS_OK;
@@ -281,6 +349,16 @@ extern "C" int sdpcs_set_weights(sdpcs_ctx* ctx, int rho, const double* blob, in
     if (ctx->d_wfrag[rho]) { cudaFree(ctx->d_wfrag[rho]); ctx->d_wfrag[rho] = nullptr; }
     CU(cudaMalloc(&ctx->d_wfrag[rho], frag.size() * sizeof(double)));
     CU(cudaMemcpyAsync(ctx->d_wfrag[rho], frag.data(), frag.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<uint8_t> img;
+    switch (rho) {
+    case 2: pack_i8<2>(blob, img); break;
+    case 3: pack_i8<3>(blob, img); break;
+    case 4: pack_i8<4>(blob, img); break;
+    case 5: pack_i8<5>(blob, img); break;
+    }
+    if (ctx->d_wi8[rho]) { cudaFree(ctx->d_wi8[rho]); ctx->d_wi8[rho] = nullptr; }
+    CU(cudaMalloc(&ctx->d_wi8[rho], img.size()));
+    CU(cudaMemcpyAsync(ctx->d_wi8[rho], img.data(), img.size(), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return SDPCS_OK;
 }
@@ -425,6 +503,59 @@ static int upload_vars(sdpcs_ctx* ctx, const double* vars_values)
 
 constexpr int NN_WARPS = 16;
 
+constexpr i64 I8_CHUNK_TILES = 65536;   // 8.4 M candidates, 2.0 GB of digit images per chunk
+
+static int ensure_tiles(sdpcs_ctx* ctx, i64 n_tiles)
+{
+    const i64 want = n_tiles * (i64)I8_TILE_BYTES;
+    if (want <= ctx->tiles_cap && ctx->d_tiles) return SDPCS_OK;
+    if (ctx->d_tiles) { cudaFree(ctx->d_tiles); ctx->d_tiles = nullptr; ctx->tiles_cap = 0; }
+    CU(cudaMalloc(&ctx->d_tiles, (size_t)want));
+    ctx->tiles_cap = want;
+    return SDPCS_OK;
+}
+
+template <int NHID>
+static int launch_mlp_i8(sdpcs_ctx* ctx, const MlpI8Args& m)
+{
+    using L = I8Smem<NHID>;
+    auto kern = k_mlp_i8<NHID>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    const unsigned grid = (unsigned)std::max<i64>(1, std::min<i64>(m.n_tiles, ctx->sms));
+    kern<<<grid, I8_THREADS, L::TOTAL, ctx->stream>>>(m);
+    CU(cudaGetLastError());
+    return SDPCS_OK;
+}
+
+// optimality measure of the N candidates described by `a` through the tcgen05 int8-sliced MLP
+template <int D>
+static int launch_nn_i8(sdpcs_ctx* ctx, const ScoreArgs& a, i64 N)
+{
+    if (!ctx->d_wi8[D]) return ctx->fail(SDPCS_ERR_STATE, "NN_" + std::to_string(D) + "D weights not set");
+    const i64 total_tiles = (N + I8_M - 1) / I8_M;
+    int rc = ensure_tiles(ctx, std::min<i64>(total_tiles, I8_CHUNK_TILES));
+    if (rc) return rc;
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_prep_i8<D>, 256, 0));
+    for (i64 c0 = 0; c0 < N; c0 += I8_CHUNK_TILES * I8_M) {
+        const i64 rows = std::min<i64>(N - c0, I8_CHUNK_TILES * I8_M);
+        const i64 nt = (rows + I8_M - 1) / I8_M;
+        PrepI8Args pa;
+        pa.s = a; pa.c0 = c0; pa.n_rows = rows; pa.tiles = ctx->d_tiles; pa.status = ctx->d_status;
+        const i64 groups = nt * (I8_M / 32);
+        const i64 pgrid = std::min<i64>((groups + 7) / 8, (i64)ctx->sms * std::max(occ, 1));
+        k_prep_i8<D><<<(unsigned)std::max<i64>(pgrid, 1), 256, 0, ctx->stream>>>(pa);
+        CU(cudaGetLastError());
+        MlpI8Args m;
+        m.wimg = ctx->d_wi8[D]; m.tiles = ctx->d_tiles; m.n_tiles = nt; m.n_rows = rows; m.out_base = c0;
+        m.pos = a.pos; m.obj = a.obj; m.dbg_z = nullptr; m.dbg_layer = -1; m.status = ctx->d_status;
+        if ((rc = launch_mlp_i8<NetCfg<D>::NHID>(ctx, m))) return rc;
+        ctx->tm.score_launches += 2;
+    }
+    ctx->i8_used = true;
+    return SDPCS_OK;
+}
+
 template <int D>
 static int launch_score(sdpcs_ctx* ctx, int want, const uint8_t* idx, const i64* pos, i64 N, i64 rank_begin)
 {
@@ -443,8 +574,12 @@ static int launch_score(sdpcs_ctx* ctx, int want, const uint8_t* idx, const i64*
         CU(cudaGetLastError());
         ctx->tm.score_launches++;
     }
-    if (want & 2) {   // K1+K2+K4: optimality measure of every candidate
-        if (!a.wfrag) return ctx->fail(SDPCS_ERR_STATE, "NN_" + std::to_string(D) + "D weights not set");
+    if ((want & 2) && !a.wfrag) return ctx->fail(SDPCS_ERR_STATE, "NN_" + std::to_string(D) + "D weights not set");
+    if ((want & 2) && ctx->params.nn_engine != SDPCS_NN_DMMA) {
+        // K1+K2 (k_prep_i8) + K4 on tcgen05 (k_mlp_i8), chunked through the layer-0 digit-image buffer
+        int rc = launch_nn_i8<D>(ctx, a, N);
+        if (rc) return rc;
+    } else if (want & 2) {   // K1+K2+K4 with FP64 DMMA: optimality measure of every candidate
         const size_t smem = (size_t)score_nn_smem_doubles<D>(NN_WARPS) * sizeof(double);
         auto kern = k_score_nn<D, NN_WARPS>;
         int occ = 0;
@@ -476,11 +611,39 @@ static int score_device(sdpcs_ctx* ctx, int want)
     ctx->tm.score_launches = 0;
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     int rc = SDPCS_OK;
-    if (ctx->mode == 1) rc = launch_score_d(ctx, ctx->rho, want, nullptr, nullptr, ctx->N, ctx->base);
-    else
-        for (int d = 2; d <= ctx->rho && rc == SDPCS_OK; ++d)
-            rc = launch_score_d(ctx, d, want, ctx->d_idx[d], ctx->d_pos[d], ctx->Nd[d], 0);
+    ctx->ev_nn = false;
+    for (int bit = 1; bit <= 2 && rc == SDPCS_OK; bit <<= 1) {   // all eigenvalue launches, then all NN launches
+        if (!(want & bit)) continue;
+        if (bit == 2) CU(cudaEventRecord(ctx->ev[6], ctx->stream));
+        if (ctx->mode == 1) rc = launch_score_d(ctx, ctx->rho, bit, nullptr, nullptr, ctx->N, ctx->base);
+        else
+            for (int d = 2; d <= ctx->rho && rc == SDPCS_OK; ++d)
+                rc = launch_score_d(ctx, d, bit, ctx->d_idx[d], ctx->d_pos[d], ctx->Nd[d], 0);
+        if (bit == 2 && rc == SDPCS_OK) { CU(cudaEventRecord(ctx->ev[7], ctx->stream)); ctx->ev_nn = true; }
+    }
     if (rc) return rc;
+    if (ctx->i8_used) {
+        // the tcgen05 pipeline reports through a device status word: 2 = an NN input outside the fixed-point
+        // range (-2, 2) (never for LP points inside the McCormick box) -> those scores are recomputed with the
+        // FP64 DMMA kernel; 1 = a pipeline barrier timed out (a bug, reported loudly)
+        ctx->i8_used = false;
+        CU(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        const int st = *ctx->h_status;
+        if (st != 0) {
+            CU(cudaMemsetAsync(ctx->d_status, 0, sizeof(int), ctx->stream));
+            if (st == 1) return ctx->fail(SDPCS_ERR_CUDA, "tcgen05 MLP pipeline timed out (k_mlp_i8)");
+            const int keep = ctx->params.nn_engine;
+            ctx->params.nn_engine = SDPCS_NN_DMMA;
+            ctx->tm.nn_fallbacks++;
+            if (ctx->mode == 1) rc = launch_score_d(ctx, ctx->rho, 2, nullptr, nullptr, ctx->N, ctx->base);
+            else
+                for (int d = 2; d <= ctx->rho && rc == SDPCS_OK; ++d)
+                    rc = launch_score_d(ctx, d, 2, ctx->d_idx[d], ctx->d_pos[d], ctx->Nd[d], 0);
+            ctx->params.nn_engine = keep;
+            if (rc) return rc;
+        }
+    }
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     ctx->ev_score = true;
     ctx->have = want & 3;
@@ -869,6 +1032,35 @@ extern "C" int sdpcs_triangles(sdpcs_ctx* ctx, const double* vars_values, int64_
     return SDPCS_OK;
 }
 
+static int read_i8_status(sdpcs_ctx* ctx, int* st)
+{
+    CU(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *st = *ctx->h_status;
+    if (*st) CU(cudaMemsetAsync(ctx->d_status, 0, sizeof(int), ctx->stream));
+    return SDPCS_OK;
+}
+
+// batched forward pass of raw input rows through the tcgen05 engine (sdpcs_nn_eval, sdpcs_nn_debug_layer)
+template <int D>
+static int launch_nn_i8_raw(sdpcs_ctx* ctx, const double* d_in, i64 m, double* d_out, double* d_z, int dbg_layer)
+{
+    for (i64 c0 = 0; c0 < m; c0 += I8_CHUNK_TILES * I8_M) {
+        const i64 rows = std::min<i64>(m - c0, I8_CHUNK_TILES * I8_M);
+        const i64 nt = (rows + I8_M - 1) / I8_M;
+        int rc = ensure_tiles(ctx, std::min<i64>((m + I8_M - 1) / I8_M, I8_CHUNK_TILES));
+        if (rc) return rc;
+        const unsigned pgrid = (unsigned)std::max<i64>(1, std::min<i64>((nt * I8_M + 255) / 256, (i64)ctx->sms * 8));
+        k_prep_i8_raw<D><<<pgrid, 256, 0, ctx->stream>>>(ctx->d_wfrag[D], d_in + c0 * NetCfg<D>::NIN, rows, ctx->d_tiles, ctx->d_status);
+        CU(cudaGetLastError());
+        MlpI8Args a;
+        a.wimg = ctx->d_wi8[D]; a.tiles = ctx->d_tiles; a.n_tiles = nt; a.n_rows = rows; a.out_base = c0;
+        a.pos = nullptr; a.obj = d_out; a.dbg_z = d_z ? d_z + c0 * 64 : nullptr; a.dbg_layer = dbg_layer; a.status = ctx->d_status;
+        if ((rc = launch_mlp_i8<NetCfg<D>::NHID>(ctx, a))) return rc;
+    }
+    return SDPCS_OK;
+}
+
 template <int D>
 static int launch_nn(sdpcs_ctx* ctx, const double* d_in, i64 m, double* d_out)
 {
@@ -894,14 +1086,62 @@ extern "C" int sdpcs_nn_eval(sdpcs_ctx* ctx, int rho, const double* inputs, int6
     double* d_in = (double*)ctx->d_scratch;
     double* d_out = d_in + (size_t)m * nin;
     CU(cudaMemcpyAsync(d_in, inputs, (size_t)m * nin * 8, cudaMemcpyHostToDevice, ctx->stream));
+    bool dmma = ctx->params.nn_engine == SDPCS_NN_DMMA;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if (dmma) {
+            switch (rho) {
+            case 2: rc = launch_nn<2>(ctx, d_in, m, d_out); break;
+            case 3: rc = launch_nn<3>(ctx, d_in, m, d_out); break;
+            case 4: rc = launch_nn<4>(ctx, d_in, m, d_out); break;
+            default: rc = launch_nn<5>(ctx, d_in, m, d_out); break;
+            }
+            if (rc) return rc;
+            break;
+        }
+        switch (rho) {
+        case 2: rc = launch_nn_i8_raw<2>(ctx, d_in, m, d_out, nullptr, -1); break;
+        case 3: rc = launch_nn_i8_raw<3>(ctx, d_in, m, d_out, nullptr, -1); break;
+        case 4: rc = launch_nn_i8_raw<4>(ctx, d_in, m, d_out, nullptr, -1); break;
+        default: rc = launch_nn_i8_raw<5>(ctx, d_in, m, d_out, nullptr, -1); break;
+        }
+        if (rc) return rc;
+        int st = 0;
+        if ((rc = read_i8_status(ctx, &st))) return rc;
+        if (st == 0) break;
+        if (st == 1) return ctx->fail(SDPCS_ERR_CUDA, "tcgen05 MLP pipeline timed out (k_mlp_i8)");
+        dmma = true;                      // inputs outside the fixed-point range: FP64 DMMA engine
+        ctx->tm.nn_fallbacks++;
+    }
+    CU(cudaMemcpyAsync(out, d_out, (size_t)m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SDPCS_OK;
+}
+
+extern "C" int sdpcs_nn_debug_layer(sdpcs_ctx* ctx, int rho, const double* inputs, int64_t m, int layer, double* out_z)
+{
+    if (!ctx || rho < 2 || rho > 5 || m <= 0 || !inputs || !out_z || layer < 0) return SDPCS_ERR_INVALID;
+    if (!ctx->d_wi8[rho]) return ctx->fail(SDPCS_ERR_STATE, "NN weights not set for this rho");
+    CU(cudaSetDevice(ctx->device));
+    const int nin = rho * (rho + 3) / 2;
+    const i64 rows = (m + I8_M - 1) / I8_M * I8_M;
+    int rc = ensure_scratch(ctx, (size_t)m * (nin + 1) * 8 + (size_t)rows * 64 * 8);
+    if (rc) return rc;
+    double* d_in = (double*)ctx->d_scratch;
+    double* d_out = d_in + (size_t)m * nin;
+    double* d_z = d_out + m;
+    CU(cudaMemcpyAsync(d_in, inputs, (size_t)m * nin * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(d_z, 0, (size_t)rows * 64 * 8, ctx->stream));
     switch (rho) {
-    case 2: rc = launch_nn<2>(ctx, d_in, m, d_out); break;
-    case 3: rc = launch_nn<3>(ctx, d_in, m, d_out); break;
-    case 4: rc = launch_nn<4>(ctx, d_in, m, d_out); break;
-    default: rc = launch_nn<5>(ctx, d_in, m, d_out); break;
+    case 2: rc = launch_nn_i8_raw<2>(ctx, d_in, m, d_out, d_z, layer); break;
+    case 3: rc = launch_nn_i8_raw<3>(ctx, d_in, m, d_out, d_z, layer); break;
+    case 4: rc = launch_nn_i8_raw<4>(ctx, d_in, m, d_out, d_z, layer); break;
+    default: rc = launch_nn_i8_raw<5>(ctx, d_in, m, d_out, d_z, layer); break;
     }
     if (rc) return rc;
-    CU(cudaMemcpyAsync(out, d_out, (size_t)m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    int st = 0;
+    if ((rc = read_i8_status(ctx, &st))) return rc;
+    if (st) return ctx->fail(SDPCS_ERR_CUDA, st == 1 ? "tcgen05 MLP pipeline timed out (k_mlp_i8)" : "NN input outside (-2, 2)");
+    CU(cudaMemcpyAsync(out_z, d_z, (size_t)m * 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return SDPCS_OK;
 }

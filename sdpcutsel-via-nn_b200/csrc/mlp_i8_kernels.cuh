@@ -1,0 +1,529 @@
+// K4 on the 5th-generation tensor cores: NN_rhoD as an error-free int8-sliced contraction (tcgen05.mma kind::i8,
+// accumulators in TMEM) instead of FP64 DMMA.  Replaces `nns[d-2][0](input_arr)` (cut_select_qp.py:579-582).
+//
+// Arithmetic (oracle/nn_i8_model.py is the bit-exact CPU statement of it):
+//   * every layer input a_k (|a| <= 1 after tansig, |p| < 2 after mapminmax) is rounded to a fixed-point integer
+//     v = rint(a * 2^51) (2^50 for layer 0), and 8v is written as 7 balanced base-256 digits (int8);
+//   * every weight row W[j,:] is scaled by a power of two >= max|W[j,:]| and rounded to 54 fractional bits, also
+//     7 balanced digits (host side, once per net);
+//   * digit-pair products are exact in the int32 tensor-core accumulators; the 28 pairs (s,t) with s + t <= 6
+//     are kept, grouped into 7 "diagonals" d = s + t (pairs on a diagonal share a TMEM accumulator);
+//   * the diagonals are recombined exactly in two int64 words, converted with one FP64 rounding, scaled and
+//     biased with one DFMA, then tansig (13 FP64 operations) as in the DMMA path.
+//   The dropped pairs are below 2^-54 of the row scale per term: the result differs from an exactly rounded FP64
+//   evaluation by about as much as two FP64 evaluations with different summation orders differ from each other
+//   (tools/i8_mlp_model.py: 4.2e-14 rms vs 2.2e-14 rms for plain FP64 at rho = 5, raw network output).
+//
+// Pipeline per CTA (one per SM, persistent over a contiguous range of 128-candidate tiles, two tiles in flight):
+//   warp 17      : TMA producer  -- cp.async.bulk of the layer-0 digit image of a tile (written by k_prep_i8)
+//   warp 16      : MMA issuer    -- one thread issues tcgen05.mma into a ring of 8 TMEM accumulators (64 columns)
+//   warps 0..15  : epilogue      -- tcgen05.ld a diagonal, int64 accumulate, DFMA + tansig, re-slice the activations
+//                                   into the next layer's A operand in shared memory (UMMA canonical K-major layout)
+//   While the epilogue warps work on tile X, the tensor core runs the next layer of tile Y.
+#pragma once
+#include "score_kernels.cuh"
+
+namespace sdpcs {
+
+constexpr int I8_NS = 7;                                  // digits per operand
+constexpr int I8_ND = 7;                                  // diagonals kept (s + t <= 6)
+constexpr int I8_M = 128;                                 // candidates per tile (UMMA M)
+constexpr int I8_N = 64;                                  // neurons (UMMA N); 50-neuron nets are zero padded
+constexpr int I8_K0 = 32;                                 // padded input width (UMMA K of layer 0)
+constexpr int I8_SLOTS = 8;                               // TMEM accumulator ring
+constexpr int I8_A0_BYTES = I8_NS * I8_M * I8_K0;         // 28672: layer-0 A image of a tile
+constexpr int I8_AH_BYTES = I8_NS * I8_M * 64;            // 57344: hidden-layer A image of a tile
+constexpr int I8_AUX_BYTES = I8_M * 16;                   // base[128], max_elem[128]
+constexpr int I8_TILE_BYTES = I8_A0_BYTES + I8_AUX_BYTES; // bytes per tile in the prep buffer
+constexpr int I8_W0_BYTES = I8_NS * I8_N * I8_K0;         // 14336
+constexpr int I8_WH_BYTES = I8_NS * I8_N * 64;            // 28672
+constexpr int I8_EPI_WARPS = 16;
+constexpr int I8_THREADS = (I8_EPI_WARPS + 2) * 32;       // 576
+constexpr int I8_NBAR = 2 * I8_SLOTS + 8;                 // slot_full[8] slot_empty[8] a0_full[2] lane_free[2] act_ready[2] y_ready[2]
+
+// instruction descriptor: D = S32, A = B = signed int8, both K-major, N = 64, M = 128 (cute::UMMA::InstrDescriptor)
+constexpr uint32_t I8_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((I8_N >> 3) << 17) | ((I8_M >> 4) << 24);
+
+// fixed-point constants
+#define I8_MAGIC52 6755399441055744.0                     /* 1.5 * 2^52 */
+#define I8_MAGIC52_BITS 0x4338000000000000ll
+#define I8_DIGIT_BIAS 0x0000808080808080ll                 /* +128 on the six low digits: balanced digits */
+
+template <int NHID>
+struct I8Smem {
+    static constexpr int W_TOTAL = I8_W0_BYTES + (NHID - 1) * I8_WH_BYTES;
+    static constexpr int OFF_A = W_TOTAL;                                  // 2 lanes x I8_AH_BYTES
+    static constexpr int OFF_AUX = OFF_A + 2 * I8_AH_BYTES;                // [lane][buf][256] doubles
+    static constexpr int OFF_PAR = OFF_AUX + 4 * I8_AUX_BYTES;
+    // parameter block (doubles): cs[NHID][64] bs[NHID][64] wout[64] misc[4] tab[256]
+    static constexpr int P_CS = 0, P_BS = NHID * 64, P_WOUT = 2 * NHID * 64, P_MISC = P_WOUT + 64, P_TAB = P_MISC + 4;
+    static constexpr int PAR = P_TAB + 256;
+    static constexpr int OFF_BAR = OFF_PAR + PAR * 8;
+    static constexpr int TOTAL = OFF_BAR + I8_NBAR * 8 + 16;
+    static constexpr int GLOBAL_BYTES = W_TOTAL + PAR * 8;                 // device blob: images then parameters
+};
+
+struct MlpI8Args {
+    const uint8_t* wimg;     // weight digit images followed by the FP64 parameter block (I8Smem::GLOBAL_BYTES)
+    const uint8_t* tiles;    // n_tiles x I8_TILE_BYTES written by k_prep_i8
+    i64 n_tiles;
+    i64 n_rows;              // valid candidates in this chunk
+    i64 out_base;            // local candidate index of row 0 of the chunk
+    const i64* pos;          // LIST mode: output position per local candidate, or nullptr
+    double* obj;
+    double* dbg_z;           // debug: scaled pre-activations of layer dbg_layer, [row][64]; nullptr in production
+    int dbg_layer;
+    int* status;             // device word: 0 ok, 1 pipeline time-out, 2 NN input outside (-2, 2)
+};
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol error ends as status = 1 and a clean kernel exit, never as a hung GPU.
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag, int* status)
+{
+    if (mbar_try(bar, parity)) return true;
+    const long long t0 = clock64();
+    while (true) {
+        if (mbar_try(bar, parity)) return true;
+        if (*abort_flag) return false;
+        if (clock64() - t0 > (1ll << 31)) {
+            *abort_flag = 1;
+            atomicCAS(status, 0, 1);
+            return false;
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major, no swizzle: 8 x 16 B core matrices, LBO = step between the two
+// 16-byte K chunks of one instruction, SBO = step between 8-row groups (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo)
+{
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_i8(uint32_t taddr, uint64_t adesc, uint64_t bdesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(taddr),
+                 "l"(adesc), "l"(bdesc), "r"(I8_IDESC), "r"(accumulate)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fixed-point slicing
+// ---------------------------------------------------------------------------------------------------
+// u = 8 * rint(a * 2^51) + I8_DIGIT_BIAS for |a| <= 1 (scale = 2^51), or with scale = 2^50 for |a| < 2.
+// bytes 0..5 of u XOR 0x80 are the six low balanced digits, byte 6 is the (signed) top digit.
+__device__ __forceinline__ unsigned long long i8_quantize(double a, double scale)
+{
+    const double q = fma(a, scale, I8_MAGIC52);
+    const long long v = __double_as_longlong(q) - I8_MAGIC52_BITS;
+    return (unsigned long long)((v << 3) + I8_DIGIT_BIAS);
+}
+
+// gather byte b of four 64-bit digit words into one 32-bit word (neuron j -> byte j), b = 0..6
+template <int B>
+__device__ __forceinline__ uint32_t i8_pack4(unsigned long long u0, unsigned long long u1, unsigned long long u2, unsigned long long u3)
+{
+    constexpr int b = B & 3;
+    const uint32_t x0 = B < 4 ? (uint32_t)u0 : (uint32_t)(u0 >> 32), x1 = B < 4 ? (uint32_t)u1 : (uint32_t)(u1 >> 32);
+    const uint32_t x2 = B < 4 ? (uint32_t)u2 : (uint32_t)(u2 >> 32), x3 = B < 4 ? (uint32_t)u3 : (uint32_t)(u3 >> 32);
+    const uint32_t t01 = __byte_perm(x0, x1, ((4 + b) << 4) | b);
+    const uint32_t t23 = __byte_perm(x2, x3, ((4 + b) << 4) | b);
+    const uint32_t w = __byte_perm(t01, t23, 0x5410);
+    return B == 6 ? w : (w ^ 0x80808080u);
+}
+
+// Write one row (candidate) of a layer-0 tile image: NIN mapminmax'ed inputs -> 7 slices x 32 digit bytes, plus aux.
+// Tile image layout: [slice s (0 = most significant)][k chunk c = k / 16][row][k % 16]; aux: base[128], max_elem[128].
+template <int NIN>
+__device__ __forceinline__ void i8_store_row(uint8_t* tile, int row, const double (&p)[NIN], double base, double max_elem,
+                                             bool valid, int* status)
+{
+    uint32_t w[I8_NS][8];
+#pragma unroll
+    for (int s = 0; s < I8_NS; ++s)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) w[s][c] = 0;
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < NIN; ++k) {
+        const double pk = valid ? p[k] : 0.0;
+        bad |= !(fabs(pk) < 2.0);
+        const unsigned long long u = i8_quantize(pk, 1125899906842624.0 /* 2^50 */);
+#pragma unroll
+        for (int b = 0; b < I8_NS; ++b) {
+            uint32_t byte = (uint32_t)(u >> (8 * b)) & 0xFFu;
+            if (b < 6) byte ^= 0x80u;
+            w[6 - b][k >> 2] |= byte << (8 * (k & 3));
+        }
+    }
+    if (bad && valid) atomicCAS(status, 0, 2);
+#pragma unroll
+    for (int s = 0; s < I8_NS; ++s) {
+        uint4* dst = reinterpret_cast<uint4*>(tile + s * (I8_M * I8_K0) + row * 16);
+        dst[0] = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+        dst[I8_M] = make_uint4(w[s][4], w[s][5], w[s][6], w[s][7]);     // + 2048 bytes: second k chunk
+    }
+    double* aux = reinterpret_cast<double*>(tile + I8_A0_BYTES);
+    aux[row] = valid ? base : 0.0;
+    aux[I8_M + row] = valid ? max_elem : 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1 + K2 + input preparation: unrank, gather x_rho / X_rho / Q_rho, max_elem, <Q~, X>, mapminmax, digit slicing.
+// Same per-candidate arithmetic as k_score_nn (cut_select_qp.py:536-538, 573-575; neural_net_3D.m:69-73).
+// Candidates [c0, c0 + n_rows) of the launch's local index space -> tiles 0.. of the prep buffer.
+// ---------------------------------------------------------------------------------------------------
+struct PrepI8Args {
+    ScoreArgs s;             // instance, cover and LP point (wfrag = DMMA blob: xoffset / gain are read from it)
+    i64 c0, n_rows;
+    uint8_t* tiles;
+    int* status;
+};
+
+template <int D>
+__global__ void __launch_bounds__(256) k_prep_i8(PrepI8Args pa)
+{
+    using C = NetCfg<D>;
+    constexpr int T = D * (D + 1) / 2;
+    const ScoreArgs& a = pa.s;
+    __shared__ double sxo[C::NIN], sgn[C::NIN];
+    if (threadIdx.x < C::NIN) {
+        sxo[threadIdx.x] = __ldg(a.wfrag + C::OFF_XOFF + threadIdx.x);
+        sgn[threadIdx.x] = __ldg(a.wfrag + C::OFF_GAIN + threadIdx.x);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const i64 warps_total = (i64)gridDim.x * (blockDim.x >> 5);
+    const i64 gw = (i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const i64 G = ((pa.n_rows + I8_M - 1) / I8_M) * (I8_M / 32);       // whole tiles: the tail rows are zero filled
+    const i64 g0 = gw * G / warps_total, g1 = (gw + 1) * G / warps_total;
+    if (g0 >= g1) return;
+    int c[D];
+    const bool all_mode = (a.idx == nullptr);
+    if (all_mode) {
+        const i64 i0 = g0 * 32 + lane;
+        if (i0 < pa.n_rows) lex_unrank<D>(a.n, (u64)(a.rank_begin + pa.c0 + i0), c);
+        else {
+#pragma unroll
+            for (int t = 0; t < D; ++t) c[t] = t;
+        }
+    }
+#pragma unroll 1
+    for (i64 g = g0; g < g1; ++g) {
+        const i64 r = g * 32 + lane;                 // row inside the chunk
+        const bool valid = r < pa.n_rows;
+        if (!all_mode) load_list_indices<D>(a.idx, pa.c0 + r, valid, c);
+        double xs[D], Xs[T], Qs[T], p[C::NIN];
+        gather_point<D>(a, c, xs, Xs);
+        int k = 0;
+        double mx = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = i; j < D; ++j) {
+                const double v = __ldg(a.Q + tri_index(a.n, c[i], c[j]));
+                Qs[k++] = v;
+                mx = fmax(mx, fabs(v));
+            }
+        double max_elem = (double)D * mx;
+        if (max_elem == 0.0) max_elem = 1.0;
+        const bool tiny = max_elem < 1e-280;
+        const double rme = fast_rcp(tiny ? 1.0 : max_elem);
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < T; ++q) {
+            Qs[q] = tiny ? __ddiv_rn(Qs[q], max_elem) : div_by(Qs[q], max_elem, rme);
+            s = __dadd_rn(s, __dmul_rn(Qs[q], Xs[q]));
+        }
+#pragma unroll
+        for (int q = 0; q < D; ++q) p[q] = __dadd_rn(__dmul_rn(__dsub_rn(xs[q], sxo[q]), sgn[q]), -1.0);
+#pragma unroll
+        for (int q = 0; q < T; ++q) p[D + q] = __dadd_rn(__dmul_rn(__dsub_rn(Qs[q], sxo[D + q]), sgn[D + q]), -1.0);
+        uint8_t* tile = pa.tiles + (r / I8_M) * (i64)I8_TILE_BYTES;
+        i8_store_row<C::NIN>(tile, (int)(r % I8_M), p, __dmul_rn(-s, max_elem), max_elem, valid, pa.status);
+        if (all_mode && g + 1 < g1) {
+            if (!(valid && lex_advance<D>(a.n, c, 32))) {
+#pragma unroll
+                for (int t = 0; t < D; ++t) c[t] = t;
+            }
+        }
+    }
+}
+
+// raw NN inputs in global memory (sdpcs_nn_eval): rows of NIN doubles -> tile images; base = 0, max_elem = 1
+template <int D>
+__global__ void __launch_bounds__(256) k_prep_i8_raw(const double* wfrag, const double* in, i64 m, uint8_t* tiles, int* status)
+{
+    using C = NetCfg<D>;
+    const i64 rows = (m + I8_M - 1) / I8_M * I8_M;
+    for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (i64)gridDim.x * blockDim.x) {
+        const bool valid = r < m;
+        double p[C::NIN];
+#pragma unroll
+        for (int q = 0; q < C::NIN; ++q) {
+            const double v = valid ? in[r * C::NIN + q] : 0.0;
+            p[q] = __dadd_rn(__dmul_rn(__dsub_rn(v, __ldg(wfrag + C::OFF_XOFF + q)), __ldg(wfrag + C::OFF_GAIN + q)), -1.0);
+        }
+        i8_store_row<C::NIN>(tiles + (r / I8_M) * (i64)I8_TILE_BYTES, (int)(r % I8_M), p, 0.0, 1.0, valid, status);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the MLP
+// ---------------------------------------------------------------------------------------------------
+template <int NHID>
+__global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
+{
+    using L = I8Smem<NHID>;
+    extern __shared__ __align__(1024) uint8_t sm[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    double* par = reinterpret_cast<double*>(sm + L::OFF_PAR);
+    volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(sm + L::OFF_BAR + I8_NBAR * 8);
+    volatile int* abort_flag = reinterpret_cast<volatile int*>(sm + L::OFF_BAR + I8_NBAR * 8 + 4);
+    const uint32_t bar0 = smem_u32(sm + L::OFF_BAR);
+    const uint32_t B_FULL = bar0, B_EMPTY = bar0 + 8 * I8_SLOTS, B_A0 = bar0 + 16 * I8_SLOTS, B_FREE = B_A0 + 16,
+                   B_ACT = B_A0 + 32, B_Y = B_A0 + 48;
+
+    const i64 t0 = a.n_tiles * blockIdx.x / gridDim.x, t1 = a.n_tiles * (blockIdx.x + 1) / gridDim.x;
+
+    // weights + parameters -> shared memory (generic proxy), barriers, TMEM
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(a.wimg);
+        uint4* dst = reinterpret_cast<uint4*>(sm);
+        for (int i = tid; i < L::W_TOTAL / 16; i += I8_THREADS) dst[i] = __ldg(src + i);
+        const double* ps = reinterpret_cast<const double*>(a.wimg + L::W_TOTAL);
+        for (int i = tid; i < L::PAR; i += I8_THREADS) par[i] = __ldg(ps + i);
+    }
+    if (tid == 0) {
+        for (int i = 0; i < I8_SLOTS; ++i) {
+            mbar_init(B_FULL + 8 * i, 1);
+            mbar_init(B_EMPTY + 8 * i, I8_EPI_WARPS);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(B_A0 + 8 * i, 1);
+            mbar_init(B_FREE + 8 * i, 1);
+            mbar_init(B_ACT + 8 * i, I8_EPI_WARPS);
+            mbar_init(B_Y + 8 * i, I8_EPI_WARPS);
+        }
+        *abort_flag = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == I8_EPI_WARPS) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr;
+    const i64 npair = (t1 - t0 + 1) / 2;
+
+    if (warp == I8_EPI_WARPS + 1) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (i64 tile = t0; tile < t1; ++tile) {
+                const int ln = (int)((tile - t0) & 1);
+                const uint32_t cnt = (uint32_t)((tile - t0) >> 1);
+                if (!mbar_wait(B_FREE + 8 * ln, (cnt & 1) ^ 1, abort_flag, a.status)) break;
+                mbar_expect_tx(B_A0 + 8 * ln, I8_TILE_BYTES);
+                const uint8_t* src = a.tiles + tile * (i64)I8_TILE_BYTES;
+                tma_load_1d(smem_u32(sm + L::OFF_A + ln * I8_AH_BYTES), src, I8_A0_BYTES, B_A0 + 8 * ln);
+                tma_load_1d(smem_u32(sm + L::OFF_AUX + (2 * ln + (cnt & 1)) * I8_AUX_BYTES), src + I8_A0_BYTES, I8_AUX_BYTES,
+                            B_A0 + 8 * ln);
+            }
+        }
+    } else if (warp == I8_EPI_WARPS) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            uint32_t ring = 0, actc[2] = {0, 0};
+            bool ok = true;
+            for (i64 p = 0; p < npair && ok; ++p)
+                for (int l = 0; l < NHID && ok; ++l)
+                    for (int ln = 0; ln < 2 && ok; ++ln) {
+                        if (t0 + 2 * p + ln >= t1) continue;
+                        if (l == 0) ok = mbar_wait(B_A0 + 8 * ln, (uint32_t)p & 1, abort_flag, a.status);
+                        else {
+                            ok = mbar_wait(B_ACT + 8 * ln, actc[ln] & 1, abort_flag, a.status);
+                            actc[ln]++;
+                        }
+                        if (!ok) break;
+                        tc_fence_after();
+                        const uint32_t abase = smem_u32(sm + L::OFF_A + ln * I8_AH_BYTES);
+                        const uint32_t wbase = smem_u32(sm + (l == 0 ? 0 : I8_W0_BYTES + (l - 1) * I8_WH_BYTES));
+                        const int ksteps = (l == 0) ? 1 : 2;
+                        const uint32_t a_slice = (l == 0) ? I8_M * I8_K0 : I8_M * 64;
+                        const uint32_t w_slice = (l == 0) ? I8_N * I8_K0 : I8_N * 64;
+                        for (int d = 0; d < I8_ND; ++d) {
+                            const uint32_t slot = ring & (I8_SLOTS - 1), use = ring / I8_SLOTS;
+                            ok = mbar_wait(B_EMPTY + 8 * slot, (use & 1) ^ 1, abort_flag, a.status);
+                            if (!ok) break;
+                            tc_fence_after();
+                            const uint32_t taddr = tmem + slot * I8_N;
+                            uint32_t acc = 0;
+                            for (int s = 0; s <= d; ++s) {
+                                const int t = d - s;
+                                for (int kk = 0; kk < ksteps; ++kk) {
+                                    const uint64_t ad = umma_desc(abase + s * a_slice + kk * 2 * (I8_M * 16), I8_M * 16, 128);
+                                    const uint64_t bd = umma_desc(wbase + t * w_slice + kk * 2 * (I8_N * 16), I8_N * 16, 128);
+                                    umma_i8(taddr, ad, bd, acc);
+                                    acc = 1;
+                                }
+                            }
+                            umma_commit(B_FULL + 8 * slot);
+                            ++ring;
+                        }
+                        if (ok && l == NHID - 1) umma_commit(B_FREE + 8 * ln);
+                    }
+        }
+    } else {
+        // ===== epilogue warps =====
+        const int q = warp & 3, cq = warp >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t tlane = (uint32_t)(q * 32) << 16;
+        const double* tab = par + L::P_TAB;
+        uint32_t ring = 0;
+        bool ok = true;
+        for (i64 p = 0; p < npair && ok; ++p)
+            for (int l = 0; l < NHID && ok; ++l)
+                for (int ln = 0; ln < 2 && ok; ++ln) {
+                    const i64 tile = t0 + 2 * p + ln;
+                    if (tile >= t1) continue;
+                    if (l == 0) {   // acquire the TMA-written aux block of this tile (read in the last layer)
+                        ok = mbar_wait(B_A0 + 8 * ln, (uint32_t)p & 1, abort_flag, a.status);
+                        ok = __all_sync(0xffffffffu, ok);
+                        if (!ok) break;
+                    }
+                    long long accL[16], accH[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) accL[j] = accH[j] = I8_MAGIC52_BITS;
+#pragma unroll
+                    for (int d = 0; d < I8_ND; ++d) {
+                        const uint32_t slot = ring & (I8_SLOTS - 1), use = ring / I8_SLOTS;
+                        if (ok) ok = mbar_wait(B_FULL + 8 * slot, use & 1, abort_flag, a.status);
+                        ok = __all_sync(0xffffffffu, ok);
+                        if (ok) {
+                            tc_fence_after();
+                            uint32_t v[16];
+                            tmem_ld16(tmem + tlane + slot * I8_N + cq * 16, v);
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(B_EMPTY + 8 * slot);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                if (d >= 3) accL[j] += (long long)(int)v[j] * (1ll << (8 * (6 - d)));
+                                else accH[j] += (long long)(int)v[j] * (1ll << (8 * (2 - d)));
+                            }
+                        }
+                        ++ring;
+                    }
+                    if (!ok) break;
+                    // value = accH * 2^32 + accL (exact integers), one rounding; z = -2 log2(e) * (W a + b)
+                    const double* cs = par + L::P_CS + l * 64 + cq * 16;
+                    const double* bs = par + L::P_BS + l * 64 + cq * 16;
+                    double act[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const double dl = __longlong_as_double(accL[j]) - I8_MAGIC52;
+                        const double dh = __longlong_as_double(accH[j]) - I8_MAGIC52;
+                        const double val = fma(dh, 4294967296.0, dl);
+                        const double z = fma(val, cs[j], bs[j]);
+                        if (a.dbg_z && l == a.dbg_layer) a.dbg_z[(tile * I8_M + row) * 64 + cq * 16 + j] = z;
+                        act[j] = tansig_scaled(z, tab);
+                    }
+                    if (l < NHID - 1) {
+                        unsigned long long u[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) u[j] = i8_quantize(act[j], 2251799813685248.0 /* 2^51 */);
+                        uint8_t* abuf = sm + L::OFF_A + ln * I8_AH_BYTES + cq * (I8_M * 16) + row * 16;
+#define I8_STORE_SLICE(B)                                                                                              \
+    *reinterpret_cast<uint4*>(abuf + (6 - B) * (I8_M * 64)) =                                                          \
+        make_uint4(i8_pack4<B>(u[0], u[1], u[2], u[3]), i8_pack4<B>(u[4], u[5], u[6], u[7]),                           \
+                   i8_pack4<B>(u[8], u[9], u[10], u[11]), i8_pack4<B>(u[12], u[13], u[14], u[15]));
+                        I8_STORE_SLICE(0) I8_STORE_SLICE(1) I8_STORE_SLICE(2) I8_STORE_SLICE(3)
+                        I8_STORE_SLICE(4) I8_STORE_SLICE(5) I8_STORE_SLICE(6)
+#undef I8_STORE_SLICE
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(B_ACT + 8 * ln);
+                    } else {
+                        // linear output layer (neural_net_3D.m:61-65, 81-85): partial dot products per column quarter
+                        const double* wout = par + L::P_WOUT + cq * 16;
+                        double part = 0.0;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) part = fma(wout[j], act[j], part);
+                        double* yp = reinterpret_cast<double*>(sm + L::OFF_A + ln * I8_AH_BYTES + I8_A0_BYTES);
+                        yp[cq * I8_M + row] = part;
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(B_Y + 8 * ln);
+                        if (cq == 0) {
+                            ok = mbar_wait(B_Y + 8 * ln, (uint32_t)p & 1, abort_flag, a.status);
+                            ok = __all_sync(0xffffffffu, ok);
+                            if (!ok) break;
+                            const double y = ((yp[row] + yp[I8_M + row]) + yp[2 * I8_M + row]) + yp[3 * I8_M + row];
+                            const double* aux = reinterpret_cast<const double*>(sm + L::OFF_AUX + (2 * ln + ((int)p & 1)) * I8_AUX_BYTES);
+                            const double bout = par[L::P_MISC], y_gain = par[L::P_MISC + 1], y_xoff = par[L::P_MISC + 2];
+                            const double nn = ((bout + y) - -1.0) / y_gain + y_xoff;
+                            const double obj = __dadd_rn(aux[row], __dmul_rn(nn, aux[I8_M + row]));
+                            const i64 r = tile * I8_M + row;
+                            if (r < a.n_rows) {
+                                const i64 gi = a.out_base + r;
+                                a.obj[a.pos ? __ldg(a.pos + gi) : gi] = obj;
+                            }
+                        }
+                    }
+                }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == I8_EPI_WARPS)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+}  // namespace sdpcs

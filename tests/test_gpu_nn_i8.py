@@ -1,0 +1,141 @@
+"""GPU tests of the tcgen05 int8-sliced NN engine (k_prep_i8 + k_mlp_i8) through the C ABI.
+
+Checked against (a) oracle/nn_i8_model.py, the integer-for-integer CPU statement of the sliced arithmetic
+(layer-0 pre-activations agree to the last bit or two, deeper layers to 1e-12), (b) the NNs.so-exact C oracle and
+the NNs.so golden vectors of the reference (tolerance 1e-11 on the raw output; north_star asks 1e-5), and
+(c) the FP64 DMMA engine on whole covers (same selection, scores within 1e-9)."""
+import numpy as np
+import pytest
+
+from oracle import cutsel_oracle as orc
+from oracle import nn_i8_model as m8
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    import sdpcutsel_via_nn_b200 as pkg
+    return pkg._capi
+
+
+def nn_inputs(rho, m, seed):
+    rng = np.random.default_rng(seed)
+    nin = rho * (rho + 3) // 2
+    return np.concatenate([rng.uniform(0, 1, (m, rho)), rng.uniform(-1.0 / rho, 1.0 / rho, (m, nin - rho))], axis=1)
+
+
+@pytest.mark.parametrize("rho", [2, 3, 4, 5])
+def test_layers_match_the_integer_model(capi, blobs, rho):
+    eng = capi.Engine(0)
+    eng.set_weights(rho, blobs[rho])
+    x = nn_inputs(rho, 700, seed=rho)
+    nhid = int(blobs[rho][1]) - 1
+    for layer in range(nhid):
+        zg = eng.nn_debug_layer(rho, x, layer)
+        _, zm = m8.forward(blobs[rho], x, layer)
+        tol = 4e-15 * np.maximum(1.0, np.abs(zm)) if layer == 0 else 1e-12
+        assert np.all(np.abs(zg - zm) <= tol), (rho, layer, np.abs(zg - zm).max())
+
+
+@pytest.mark.parametrize("rho", [2, 3, 4, 5])
+@pytest.mark.parametrize("m", [1, 127, 128, 129, 383, 40000])
+def test_nn_eval_ragged_sizes(capi, blobs, rho, m):
+    """tile tails, odd tile counts per CTA (one lane idle) and many CTAs."""
+    eng = capi.Engine(0)
+    eng.set_weights(rho, blobs[rho])
+    x = nn_inputs(rho, m, seed=100 + m)
+    want = orc.nn_eval(blobs[rho], x)
+    eng.set_params(nn_engine=capi.NN_TCGEN05)
+    y = eng.nn_eval(rho, x)
+    assert np.abs(y - want).max() < 1e-11
+    eng.set_params(nn_engine=capi.NN_DMMA)
+    y2 = eng.nn_eval(rho, x)
+    assert np.abs(y - y2).max() < 1e-11
+    assert eng.timings()["nn_fallbacks"] == 0
+
+
+@pytest.mark.parametrize("d", [2, 3, 4, 5])
+def test_golden_NNs_so_vectors(capi, blobs, golden, d):
+    eng = capi.Engine(0)
+    eng.set_weights(d, blobs[d])
+    eng.set_params(nn_engine=capi.NN_TCGEN05)
+    y = eng.nn_eval(d, golden["nn%d_in" % d])
+    assert np.abs(y - golden["nn%d_out" % d]).max() < 1e-11
+
+
+def test_saturated_and_extreme_inputs(capi, blobs):
+    """x = 0 / 1 exactly and Q~ = +-1/rho hit the ends of the fixed-point range (|p| = 1, tansig saturation)."""
+    rho = 5
+    eng = capi.Engine(0)
+    eng.set_weights(rho, blobs[rho])
+    nin = 20
+    rows = [np.zeros(nin), np.ones(nin) / rho, -np.ones(nin) / rho]
+    r = np.ones(nin) / rho
+    r[:rho] = 1.0
+    rows.append(r)
+    r = -np.ones(nin) / rho
+    r[:rho] = 0.0
+    rows.append(r)
+    x = np.array(rows)
+    y = eng.nn_eval(rho, x)
+    assert np.abs(y - orc.nn_eval(blobs[rho], x)).max() < 1e-11
+    assert eng.timings()["nn_fallbacks"] == 0
+
+
+def test_out_of_range_inputs_fall_back_to_dmma(capi, blobs):
+    """mapminmax'ed inputs outside (-2, 2) cannot be sliced: the call re-scores with the FP64 DMMA engine."""
+    rho = 3
+    eng = capi.Engine(0)
+    eng.set_weights(rho, blobs[rho])
+    x = nn_inputs(rho, 300, seed=9)
+    x[17, 1] = 40.0
+    y = eng.nn_eval(rho, x)
+    assert np.abs(y - orc.nn_eval(blobs[rho], x)).max() < 1e-10
+    assert eng.timings()["nn_fallbacks"] == 1
+
+
+@pytest.mark.parametrize("rho", [3, 4, 5])
+def test_cover_scores_both_engines(capi, blobs, rho):
+    """whole all-subsets cover: tcgen05 and DMMA engines give the same combined selection and scores within 1e-9."""
+    n = 30 if rho < 5 else 24
+    Q_arr, adj = orc.boxqp_arrays(orc.synth_instance(n, 0.7, seed=21))
+    vv = orc.synth_point(n, seed=5)
+    out = {}
+    for name, engine in (("i8", capi.NN_TCGEN05), ("dmma", capi.NN_DMMA)):
+        eng = capi.Engine(0)
+        eng.set_params(nn_engine=engine)
+        eng.set_weights(rho, blobs[rho])
+        eng.set_instance(n, Q_arr)
+        eng.set_cover_all(rho)
+        res = eng.select(4, vv, 400)
+        lam, obj = eng.scores()
+        out[name] = (res, lam, obj)
+        assert eng.timings()["nn_fallbacks"] == 0
+    idx = orc.cover_all(n, rho)
+    lam_o, obj_o = orc.score_cover(Q_arr, n, idx, np.full(idx.shape[0], rho), vv, {rho: blobs[rho]})
+    assert np.abs(out["i8"][2] - obj_o).max() < 1e-9
+    assert np.abs(out["i8"][2] - out["dmma"][2]).max() < 1e-9
+    assert np.array_equal(out["i8"][0]["idx"], out["dmma"][0]["idx"])
+    ns, order, score = orc.select_comb(obj_o, lam_o, 400)
+    assert np.array_equal(out["i8"][0]["idx"], order[:400])
+    assert out["i8"][0]["new_strat"] == ns
+
+
+def test_sharded_rank_ranges_are_consistent(capi, blobs):
+    """a shard starting in the middle of the rank space (chunk offsets, unranking from rank_begin + c0)."""
+    n, rho = 26, 5
+    Q_arr, adj = orc.boxqp_arrays(orc.synth_instance(n, 0.75, seed=3))
+    vv = orc.synth_point(n, seed=4)
+    eng = capi.Engine(0)
+    eng.set_weights(rho, blobs[rho])
+    eng.set_instance(n, Q_arr)
+    eng.set_cover_all(rho)
+    eng.score(vv, 2)
+    _, full = eng.scores(lam=False)
+    N = full.size
+    r0, r1 = N // 3 + 5, 2 * N // 3 + 77
+    eng.set_cover_all(rho, r0, r1)
+    eng.score(vv, 2)
+    _, part = eng.scores(lam=False)
+    assert np.array_equal(part, full[r0:r1])
