@@ -5,7 +5,8 @@ kernel can be checked layer by layer (``sdpcs_nn_debug_layer``):
 
 * weights: row ``j`` of a layer is scaled by ``2^e >= max|W[j,:]|``, ``wint = rint(W * 2^(54-e))``, 7 balanced
   base-256 digits (most significant first);
-* layer inputs: ``v = rint(a * 2^51)`` (``2^50`` for the mapminmax'ed network inputs), digits of ``8 v``;
+* layer inputs: ``v = rint(a * 2^51)`` (``2^50`` for the mapminmax'ed network inputs); the two's complement word
+  ``8 v`` is cut into six unsigned low digits and one signed top digit (unsigned-A / signed-A MMAs on the GPU);
 * digit-pair products on the diagonals ``s + t <= 6`` are summed exactly (int32 on the GPU), recombined as
   ``H * 2^32 + L`` with one FP64 rounding, ``z = fma(val, cs, bs)`` with ``cs = 2^(e-54-ea+48) * (-2 log2 e)``;
 * ``tansig`` from the scaled pre-activation; the output layer and ``mapminmax`` reverse in FP64
@@ -43,6 +44,14 @@ def digits(v):
     return out[::-1]
 
 
+def digits_twos(v):
+    """int64 array -> six unsigned low digits [0, 255] and one signed top digit, most significant first."""
+    u = v.astype(np.int64)
+    out = [(u >> (8 * b)) & 0xFF for b in range(NS - 1)] + [u >> (8 * (NS - 1))]
+    assert np.abs(out[-1]).max() <= 128
+    return out[::-1]
+
+
 def pack_layer(W, b, ea, K):
     """-> (digit slices [NS] of shape (64, K), cs[64], bs[64])"""
     h, cols = W.shape
@@ -60,7 +69,7 @@ def pack_layer(W, b, ea, K):
 def layer_z(a, wd, cs, bs, scale_log2):
     """a: (m, K) layer inputs; returns the scaled pre-activations z (m, 64) exactly as the kernel forms them."""
     v = np.rint(a * 2.0 ** scale_log2).astype(np.int64) * 8
-    ad = digits(v)
+    ad = digits_twos(v)
     H = np.zeros((a.shape[0], 64), dtype=np.int64)
     L = np.zeros((a.shape[0], 64), dtype=np.int64)
     for d in range(DMAX + 1):

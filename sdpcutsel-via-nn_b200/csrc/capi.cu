@@ -210,8 +210,8 @@ static void pack_i8(const double* blob, std::vector<uint8_t>& out)
                 }
             }
             // z = -2 log2(e) * (W a + b);  W a = 2^(e - 54) * 2^-ea * 2^48 * (sum of the kept digit-pair diagonals)
-            par[L::P_CS + l * 64 + j] = std::ldexp(1.0, e - 54 - ea + 48) * SDPCS_TANSIG_SCALE;
-            par[L::P_BS + l * 64 + j] = (j < h) ? SDPCS_TANSIG_SCALE * B[l][j] : 0.0;
+            par[L::P_CS + 2 * (l * 64 + j)] = std::ldexp(1.0, e - 54 - ea + 48) * SDPCS_TANSIG_SCALE;
+            par[L::P_CS + 2 * (l * 64 + j) + 1] = (j < h) ? SDPCS_TANSIG_SCALE * B[l][j] : 0.0;
         }
     }
     for (int j = 0; j < h; ++j) par[L::P_WOUT + j] = W[NL - 1][j];
@@ -1179,3 +1179,14 @@ extern "C" int sdpcs_fp64_peak(sdpcs_ctx* ctx, double* dfma_tflops, double* dmma
     if (dmma_tflops) *dmma_tflops = best[1];
     return SDPCS_OK;
 }
+
+#ifdef SDPCS_I8_TRACE
+// trace build only (tools/i8_trace.py): clock64 stamps of CTA 0, [warp 0..17][step][4]
+extern "C" int sdpcs_i8_trace_read(long long* out, int64_t cap)
+{
+    const size_t bytes = sizeof(long long) * (I8_EPI_WARPS + 2) * I8_TRACE_STEPS * 4;
+    if ((size_t)cap * sizeof(long long) < bytes) return SDPCS_ERR_INVALID;
+    if (cudaMemcpyFromSymbol(out, g_i8_trace, bytes) != cudaSuccess) return SDPCS_ERR_CUDA;
+    return (I8_EPI_WARPS + 2) * I8_TRACE_STEPS * 4;
+}
+#endif

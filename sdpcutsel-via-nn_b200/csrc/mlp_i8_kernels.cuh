@@ -3,9 +3,11 @@
 //
 // Arithmetic (oracle/nn_i8_model.py is the bit-exact CPU statement of it):
 //   * every layer input a_k (|a| <= 1 after tansig, |p| < 2 after mapminmax) is rounded to a fixed-point integer
-//     v = rint(a * 2^51) (2^50 for layer 0), and 8v is written as 7 balanced base-256 digits (int8);
-//   * every weight row W[j,:] is scaled by a power of two >= max|W[j,:]| and rounded to 54 fractional bits, also
-//     7 balanced digits (host side, once per net);
+//     v = rint(a * 2^51) (2^50 for layer 0), and the two's complement word 8v is cut into 7 base-256 digits: six
+//     unsigned low digits and one signed top digit (no re-balancing arithmetic in the epilogue; the MMAs on the top
+//     slice use a signed A operand, the others an unsigned one);
+//   * every weight row W[j,:] is scaled by a power of two >= max|W[j,:]| and rounded to 54 fractional bits, written
+//     as 7 balanced digits (host side, once per net);
 //   * digit-pair products are exact in the int32 tensor-core accumulators; the 28 pairs (s,t) with s + t <= 6
 //     are kept, grouped into 7 "diagonals" d = s + t (pairs on a diagonal share a TMEM accumulator);
 //   * the diagonals are recombined exactly in two int64 words, converted with one FP64 rounding, scaled and
@@ -16,7 +18,8 @@
 //
 // Pipeline per CTA (one per SM, persistent over a contiguous range of 128-candidate tiles, two tiles in flight):
 //   warp 17      : TMA producer  -- cp.async.bulk of the layer-0 digit image of a tile (written by k_prep_i8)
-//   warp 16      : MMA issuer    -- one thread issues tcgen05.mma into a ring of 8 TMEM accumulators (64 columns)
+//   warp 16      : MMA issuer    -- one thread issues the 28 digit-pair tcgen05.mma chains of a layer into 7 TMEM
+//                                   accumulators (one per diagonal, 64 columns each), one commit per layer
 //   warps 0..15  : epilogue      -- tcgen05.ld a diagonal, int64 accumulate, DFMA + tansig, re-slice the activations
 //                                   into the next layer's A operand in shared memory (UMMA canonical K-major layout)
 //   While the epilogue warps work on tile X, the tensor core runs the next layer of tile Y.
@@ -41,13 +44,14 @@ constexpr int I8_EPI_WARPS = 16;
 constexpr int I8_THREADS = (I8_EPI_WARPS + 2) * 32;       // 576
 constexpr int I8_NBAR = 2 * I8_SLOTS + 8;                 // slot_full[8] slot_empty[8] a0_full[2] lane_free[2] act_ready[2] y_ready[2]
 
-// instruction descriptor: D = S32, A = B = signed int8, both K-major, N = 64, M = 128 (cute::UMMA::InstrDescriptor)
-constexpr uint32_t I8_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((I8_N >> 3) << 17) | ((I8_M >> 4) << 24);
+// instruction descriptor: D = S32, B = signed int8, A = signed (top slice) or unsigned int8, both K-major, N = 64,
+// M = 128 (cute::UMMA::InstrDescriptor)
+constexpr uint32_t I8_IDESC_U = (2u << 4) | (0u << 7) | (1u << 10) | ((I8_N >> 3) << 17) | ((I8_M >> 4) << 24);
+constexpr uint32_t I8_IDESC_S = I8_IDESC_U | (1u << 7);
 
 // fixed-point constants
 #define I8_MAGIC52 6755399441055744.0                     /* 1.5 * 2^52 */
 #define I8_MAGIC52_BITS 0x4338000000000000ll
-#define I8_DIGIT_BIAS 0x0000808080808080ll                 /* +128 on the six low digits: balanced digits */
 
 template <int NHID>
 struct I8Smem {
@@ -55,7 +59,7 @@ struct I8Smem {
     static constexpr int OFF_A = W_TOTAL;                                  // 2 lanes x I8_AH_BYTES
     static constexpr int OFF_AUX = OFF_A + 2 * I8_AH_BYTES;                // [lane][buf][256] doubles
     static constexpr int OFF_PAR = OFF_AUX + 4 * I8_AUX_BYTES;
-    // parameter block (doubles): cs[NHID][64] bs[NHID][64] wout[64] misc[4] tab[256]
+    // parameter block (doubles): (cs, bs)[NHID][64] interleaved pairs, wout[64] misc[4] tab[256]
     static constexpr int P_CS = 0, P_BS = NHID * 64, P_WOUT = 2 * NHID * 64, P_MISC = P_WOUT + 64, P_TAB = P_MISC + 4;
     static constexpr int PAR = P_TAB + 256;
     static constexpr int OFF_BAR = OFF_PAR + PAR * 8;
@@ -75,6 +79,20 @@ struct MlpI8Args {
     int dbg_layer;
     int* status;             // device word: 0 ok, 1 pipeline time-out, 2 NN input outside (-2, 2)
 };
+
+// Optional pipeline trace (tools/i8_trace.py builds a second library with -DSDPCS_I8_TRACE): CTA 0 stamps clock64 at
+// four points of steps 64 .. 64 + I8_TRACE_STEPS of every warp.  Compiled out of the product library.
+#ifdef SDPCS_I8_TRACE
+constexpr int I8_TRACE_STEPS = 96;
+__device__ long long g_i8_trace[I8_EPI_WARPS + 2][I8_TRACE_STEPS][4];
+#define I8_STAMP(STEP, K)                                                                                              \
+    do {                                                                                                               \
+        if (blockIdx.x == 0 && lane == 0 && (STEP) - 64u < (uint32_t)I8_TRACE_STEPS)                                   \
+            g_i8_trace[warp][(STEP) - 64u][K] = clock64();                                                              \
+    } while (0)
+#else
+#define I8_STAMP(STEP, K) do { } while (0)
+#endif
 
 // ---------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -117,12 +135,40 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatil
         }
     }
 }
+// same, for the producer warp that runs a whole tile ahead: back off between polls so that it does not take
+// issue slots from the epilogue warps of its scheduler
+__device__ __forceinline__ bool mbar_wait_relaxed(uint32_t bar, uint32_t parity, volatile int* abort_flag, int* status)
+{
+    if (mbar_try(bar, parity)) return true;
+    const long long t0 = clock64();
+    while (true) {
+        __nanosleep(200);
+        if (mbar_try(bar, parity)) return true;
+        if (*abort_flag) return false;
+        if (clock64() - t0 > (1ll << 31)) {
+            *abort_flag = 1;
+            atomicCAS(status, 0, 1);
+            return false;
+        }
+    }
+}
+// one lane of a converged warp (elect.sync): the compiler then knows the branch is single-threaded and keeps
+// tcgen05 / TMA operands in uniform registers instead of emitting a per-lane waterfall loop
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred)::"memory");
+    return pred != 0;
+}
 __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// named barrier among the four epilogue warps of one TMEM lane quarter (they share an SM sub-partition): keeps them
+// in lock-step so that no warp is left to finish a step alone at single-warp issue rate
+__device__ __forceinline__ void quarter_sync(int q) { asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -133,10 +179,10 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint
 {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
-__device__ __forceinline__ void umma_i8(uint32_t taddr, uint64_t adesc, uint64_t bdesc, uint32_t accumulate)
+__device__ __forceinline__ void umma_i8(uint32_t taddr, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(taddr),
-                 "l"(adesc), "l"(bdesc), "r"(I8_IDESC), "r"(accumulate)
+                 "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
                  : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar)
@@ -153,16 +199,81 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld8_async(uint32_t taddr, uint32_t (&v)[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// tansig_scaled (device_math.cuh) on W independent arguments, written stage by stage so that the W dependency
+// chains are interleaved in the instruction stream (the epilogue has only four warps per scheduler: the FP64
+// latency has to be covered by instruction-level parallelism).
+template <int W>
+__device__ __forceinline__ void tansig_scaled_vec(const double (&zs)[W], double (&out)[W], const double* __restrict__ T)
+{
+    const double A1 = 0.6931471805599453094, A2 = 0.2402265069591007123, A3 = 0.0555041086648215800,
+                 A4 = 0.0096181291076284772;
+    const double MAGIC = 26388279066624.0;  // 1.5 * 2^44: ulp = 2^-8
+    int sgn[W], idx[W];
+    double w[W], s[W], q[W], t[W], d[W], y0[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        const uint32_t hi = (uint32_t)__double2hiint(zs[i]);
+        sgn[i] = (int)(hi & 0x80000000u);
+        // -|z|, clamped at -1000 on the high word (negative doubles order like unsigned integers)
+        w[i] = __hiloint2double((int)min(hi | 0x80000000u, 0xC08F4000u), __double2loint(zs[i]));
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        const double kf = w[i] + MAGIC;
+        idx[i] = __double2loint(kf);
+        s[i] = w[i] - (kf - MAGIC);
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i) q[i] = fma(A4, s[i], A3);
+#pragma unroll
+    for (int i = 0; i < W; ++i) q[i] = fma(q[i], s[i], A2);
+#pragma unroll
+    for (int i = 0; i < W; ++i) q[i] = fma(q[i], s[i], A1);
+#pragma unroll
+    for (int i = 0; i < W; ++i) q[i] = q[i] * s[i];
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        const double Tj = T[idx[i] & 255];
+        const double t0 = fma(Tj, q[i], Tj);
+        t[i] = __hiloint2double(__double2hiint(t0) + ((idx[i] >> 8) << 20), __double2loint(t0));
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        d[i] = 1.0 + t[i];                      // in (1, 2]
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0[i]) : "d"(d[i]));   // MUFU.RCP64H: ~20-bit seed, cubic step below
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        const double e = fma(-d[i], y0[i], 1.0);
+        q[i] = fma(e, e, e);
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        const double y = fma(y0[i], q[i], y0[i]);
+        const double r = fma(2.0, y, -1.0);
+        out[i] = __hiloint2double(__double2hiint(r) ^ (sgn[i] ^ 0x80000000), __double2loint(r));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // fixed-point slicing
 // ---------------------------------------------------------------------------------------------------
-// u = 8 * rint(a * 2^51) + I8_DIGIT_BIAS for |a| <= 1 (scale = 2^51), or with scale = 2^50 for |a| < 2.
-// bytes 0..5 of u XOR 0x80 are the six low balanced digits, byte 6 is the (signed) top digit.
+// u = 8 * rint(a * 2^51) for |a| <= 1 (scale = 2^51), or with scale = 2^50 for |a| < 2, as a two's complement word:
+// bytes 0..5 are the six low digits (unsigned), byte 6 is the signed top digit.
 __device__ __forceinline__ unsigned long long i8_quantize(double a, double scale)
 {
     const double q = fma(a, scale, I8_MAGIC52);
     const long long v = __double_as_longlong(q) - I8_MAGIC52_BITS;
-    return (unsigned long long)((v << 3) + I8_DIGIT_BIAS);
+    return (unsigned long long)(v << 3);
 }
 
 // gather byte b of four 64-bit digit words into one 32-bit word (neuron j -> byte j), b = 0..6
@@ -174,8 +285,7 @@ __device__ __forceinline__ uint32_t i8_pack4(unsigned long long u0, unsigned lon
     const uint32_t x2 = B < 4 ? (uint32_t)u2 : (uint32_t)(u2 >> 32), x3 = B < 4 ? (uint32_t)u3 : (uint32_t)(u3 >> 32);
     const uint32_t t01 = __byte_perm(x0, x1, ((4 + b) << 4) | b);
     const uint32_t t23 = __byte_perm(x2, x3, ((4 + b) << 4) | b);
-    const uint32_t w = __byte_perm(t01, t23, 0x5410);
-    return B == 6 ? w : (w ^ 0x80808080u);
+    return __byte_perm(t01, t23, 0x5410);
 }
 
 // Write one row (candidate) of a layer-0 tile image: NIN mapminmax'ed inputs -> 7 slices x 32 digit bytes, plus aux.
@@ -197,8 +307,7 @@ __device__ __forceinline__ void i8_store_row(uint8_t* tile, int row, const doubl
         const unsigned long long u = i8_quantize(pk, 1125899906842624.0 /* 2^50 */);
 #pragma unroll
         for (int b = 0; b < I8_NS; ++b) {
-            uint32_t byte = (uint32_t)(u >> (8 * b)) & 0xFFu;
-            if (b < 6) byte ^= 0x80u;
+            const uint32_t byte = (uint32_t)(u >> (8 * b)) & 0xFFu;
             w[6 - b][k >> 2] |= byte << (8 * (k & 3));
         }
     }
@@ -366,138 +475,188 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
     const i64 npair = (t1 - t0 + 1) / 2;
 
     if (warp == I8_EPI_WARPS + 1) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            for (i64 tile = t0; tile < t1; ++tile) {
-                const int ln = (int)((tile - t0) & 1);
-                const uint32_t cnt = (uint32_t)((tile - t0) >> 1);
-                if (!mbar_wait(B_FREE + 8 * ln, (cnt & 1) ^ 1, abort_flag, a.status)) break;
+        // ===== TMA producer (whole warp walks the tile list, one elected lane issues the bulk copies) =====
+        bool ok = true;
+        for (i64 tile = t0; tile < t1 && ok; ++tile) {
+            const int ln = (int)((tile - t0) & 1);
+            const uint32_t cnt = (uint32_t)((tile - t0) >> 1);
+            ok = mbar_wait_relaxed(B_FREE + 8 * ln, (cnt & 1) ^ 1, abort_flag, a.status);
+            ok = __all_sync(0xffffffffu, ok);
+            if (!ok) break;
+            if (elect_one()) {
                 mbar_expect_tx(B_A0 + 8 * ln, I8_TILE_BYTES);
                 const uint8_t* src = a.tiles + tile * (i64)I8_TILE_BYTES;
                 tma_load_1d(smem_u32(sm + L::OFF_A + ln * I8_AH_BYTES), src, I8_A0_BYTES, B_A0 + 8 * ln);
                 tma_load_1d(smem_u32(sm + L::OFF_AUX + (2 * ln + (cnt & 1)) * I8_AUX_BYTES), src + I8_A0_BYTES, I8_AUX_BYTES,
                             B_A0 + 8 * ln);
             }
+            __syncwarp();
         }
     } else if (warp == I8_EPI_WARPS) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            uint32_t ring = 0, actc[2] = {0, 0};
-            bool ok = true;
-            for (i64 p = 0; p < npair && ok; ++p)
-                for (int l = 0; l < NHID && ok; ++l)
-                    for (int ln = 0; ln < 2 && ok; ++ln) {
-                        if (t0 + 2 * p + ln >= t1) continue;
-                        if (l == 0) ok = mbar_wait(B_A0 + 8 * ln, (uint32_t)p & 1, abort_flag, a.status);
-                        else {
-                            ok = mbar_wait(B_ACT + 8 * ln, actc[ln] & 1, abort_flag, a.status);
-                            actc[ln]++;
-                        }
-                        if (!ok) break;
-                        tc_fence_after();
-                        const uint32_t abase = smem_u32(sm + L::OFF_A + ln * I8_AH_BYTES);
-                        const uint32_t wbase = smem_u32(sm + (l == 0 ? 0 : I8_W0_BYTES + (l - 1) * I8_WH_BYTES));
-                        const int ksteps = (l == 0) ? 1 : 2;
-                        const uint32_t a_slice = (l == 0) ? I8_M * I8_K0 : I8_M * 64;
-                        const uint32_t w_slice = (l == 0) ? I8_N * I8_K0 : I8_N * 64;
-                        for (int d = 0; d < I8_ND; ++d) {
-                            const uint32_t slot = ring & (I8_SLOTS - 1), use = ring / I8_SLOTS;
-                            ok = mbar_wait(B_EMPTY + 8 * slot, (use & 1) ^ 1, abort_flag, a.status);
-                            if (!ok) break;
-                            tc_fence_after();
-                            const uint32_t taddr = tmem + slot * I8_N;
-                            uint32_t acc = 0;
-                            for (int s = 0; s <= d; ++s) {
-                                const int t = d - s;
-                                for (int kk = 0; kk < ksteps; ++kk) {
-                                    const uint64_t ad = umma_desc(abase + s * a_slice + kk * 2 * (I8_M * 16), I8_M * 16, 128);
-                                    const uint64_t bd = umma_desc(wbase + t * w_slice + kk * 2 * (I8_N * 16), I8_N * 16, 128);
-                                    umma_i8(taddr, ad, bd, acc);
-                                    acc = 1;
-                                }
-                            }
-                            umma_commit(B_FULL + 8 * slot);
-                            ++ring;
-                        }
-                        if (ok && l == NHID - 1) umma_commit(B_FREE + 8 * ln);
+        // ===== MMA issuer (whole warp walks the schedule and waits, one elected lane issues) =====
+        // One accumulator stage: diagonal d lives in TMEM columns [64 d, 64 d + 64).  The stage is handed to the
+        // epilogue with one commit per step and handed back once every epilogue warp has read it, so the MMAs of
+        // step n+1 (other tile) run while the epilogue warps finalize step n.
+        uint32_t step = 0, actc[2] = {0, 0};
+        bool ok = true;
+        for (i64 p = 0; p < npair && ok; ++p)
+            for (int l = 0; l < NHID && ok; ++l)
+                for (int ln = 0; ln < 2 && ok; ++ln) {
+                    if (t0 + 2 * p + ln >= t1) continue;
+                    I8_STAMP(step, 0);
+                    if (l == 0) ok = mbar_wait(B_A0 + 8 * ln, (uint32_t)p & 1, abort_flag, a.status);
+                    else {
+                        ok = mbar_wait(B_ACT + 8 * ln, actc[ln] & 1, abort_flag, a.status);
+                        actc[ln]++;
                     }
-        }
+                    I8_STAMP(step, 1);
+                    if (ok) ok = mbar_wait(B_EMPTY, (step & 1) ^ 1, abort_flag, a.status);
+                    ok = __all_sync(0xffffffffu, ok);
+                    if (!ok) break;
+                    I8_STAMP(step, 2);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        // A: 8 x 16 B core matrices, K chunks 2048 B apart (128 rows x 16 B), 8-row groups 128 B apart
+                        // W: K chunks 1024 B apart (64 rows x 16 B)
+                        const uint64_t ad0 = umma_desc(smem_u32(sm + L::OFF_A + ln * I8_AH_BYTES), I8_M * 16, 128);
+                        const uint64_t bd0 = umma_desc(smem_u32(sm + (l == 0 ? 0 : I8_W0_BYTES + (l - 1) * I8_WH_BYTES)), I8_N * 16, 128);
+                        if (l == 0) {
+#pragma unroll
+                            for (int d = 0; d < I8_ND; ++d)
+#pragma unroll
+                                for (int sd = 0; sd <= d; ++sd)
+                                    umma_i8(tmem + d * I8_N, ad0 + (uint64_t)((sd * (I8_M * I8_K0)) >> 4),
+                                            bd0 + (uint64_t)(((d - sd) * (I8_N * I8_K0)) >> 4), sd ? I8_IDESC_U : I8_IDESC_S, sd > 0);
+                        } else {
+#pragma unroll
+                            for (int d = 0; d < I8_ND; ++d)
+#pragma unroll
+                                for (int sd = 0; sd <= d; ++sd)
+#pragma unroll
+                                    for (int kk = 0; kk < 2; ++kk)
+                                        umma_i8(tmem + d * I8_N, ad0 + (uint64_t)((sd * (I8_M * 64) + kk * 2 * (I8_M * 16)) >> 4),
+                                                bd0 + (uint64_t)(((d - sd) * (I8_N * 64) + kk * 2 * (I8_N * 16)) >> 4),
+                                                sd ? I8_IDESC_U : I8_IDESC_S, (sd | kk) > 0);
+                        }
+                        umma_commit(B_FULL);
+                        if (l == NHID - 1) umma_commit(B_FREE + 8 * ln);
+                    }
+                    __syncwarp();
+                    I8_STAMP(step, 3);
+                    ++step;
+                }
     } else {
         // ===== epilogue warps =====
         const int q = warp & 3, cq = warp >> 2;
         const int row = q * 32 + lane;
-        const uint32_t tlane = (uint32_t)(q * 32) << 16;
+        const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + cq * 16;
         const double* tab = par + L::P_TAB;
-        uint32_t ring = 0;
+        uint32_t step = 0;
         bool ok = true;
         for (i64 p = 0; p < npair && ok; ++p)
             for (int l = 0; l < NHID && ok; ++l)
                 for (int ln = 0; ln < 2 && ok; ++ln) {
                     const i64 tile = t0 + 2 * p + ln;
                     if (tile >= t1) continue;
-                    if (l == 0) {   // acquire the TMA-written aux block of this tile (read in the last layer)
+                    I8_STAMP(step, 0);
+                    if (l == 0)   // acquire the TMA-written aux block of this tile (read in the last layer)
                         ok = mbar_wait(B_A0 + 8 * ln, (uint32_t)p & 1, abort_flag, a.status);
-                        ok = __all_sync(0xffffffffu, ok);
-                        if (!ok) break;
-                    }
-                    long long accL[16], accH[16];
+                    if (ok) ok = mbar_wait(B_FULL, step & 1, abort_flag, a.status);
+                    ok = __all_sync(0xffffffffu, ok);
+                    if (!ok) break;
+                    I8_STAMP(step, 1);
+                    tc_fence_after();
+#ifdef SDPCS_I8_QSYNC
+                    if ((step & (SDPCS_I8_QSYNC - 1)) == 0) quarter_sync(q);
+#endif
+                    const double2* csbs = reinterpret_cast<const double2*>(par + L::P_CS) + l * 64 + cq * 16;   // (cs, bs) pairs
+                    const double* wout = par + L::P_WOUT + cq * 16;
+                    // Phase 1: read the seven diagonals (two batches of TMEM loads, 8 neurons each), recombine them
+                    // exactly in int64 and reduce to the FP64 pre-activations.  The accumulator stage is handed back
+                    // to the MMA issuer as soon as the second batch is in registers.
+                    double z[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) accL[j] = accH[j] = I8_MAGIC52_BITS;
-#pragma unroll
-                    for (int d = 0; d < I8_ND; ++d) {
-                        const uint32_t slot = ring & (I8_SLOTS - 1), use = ring / I8_SLOTS;
-                        if (ok) ok = mbar_wait(B_FULL + 8 * slot, use & 1, abort_flag, a.status);
-                        ok = __all_sync(0xffffffffu, ok);
-                        if (ok) {
-                            tc_fence_after();
-                            uint32_t v[16];
-                            tmem_ld16(tmem + tlane + slot * I8_N + cq * 16, v);
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t v0[8], v1[8], v2[8], v3[8], v4[8], v5[8], v6[8];
+                        tmem_ld8_async(tbase + 0 * I8_N + half * 8, v0);
+                        tmem_ld8_async(tbase + 1 * I8_N + half * 8, v1);
+                        tmem_ld8_async(tbase + 2 * I8_N + half * 8, v2);
+                        tmem_ld8_async(tbase + 3 * I8_N + half * 8, v3);
+                        tmem_ld8_async(tbase + 4 * I8_N + half * 8, v4);
+                        tmem_ld8_async(tbase + 5 * I8_N + half * 8, v5);
+                        tmem_ld8_async(tbase + 6 * I8_N + half * 8, v6);
+                        tmem_wait_ld();
+                        if (half == 1) {
                             tc_fence_before();
                             __syncwarp();
-                            if (lane == 0) mbar_arrive(B_EMPTY + 8 * slot);
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                if (d >= 3) accL[j] += (long long)(int)v[j] * (1ll << (8 * (6 - d)));
-                                else accH[j] += (long long)(int)v[j] * (1ll << (8 * (2 - d)));
-                            }
+                            if (lane == 0) mbar_arrive(B_EMPTY);
+                            I8_STAMP(step, 2);
                         }
-                        ++ring;
-                    }
-                    if (!ok) break;
-                    // value = accH * 2^32 + accL (exact integers), one rounding; z = -2 log2(e) * (W a + b)
-                    const double* cs = par + L::P_CS + l * 64 + cq * 16;
-                    const double* bs = par + L::P_BS + l * 64 + cq * 16;
-                    double act[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const double dl = __longlong_as_double(accL[j]) - I8_MAGIC52;
-                        const double dh = __longlong_as_double(accH[j]) - I8_MAGIC52;
-                        const double val = fma(dh, 4294967296.0, dl);
-                        const double z = fma(val, cs[j], bs[j]);
-                        if (a.dbg_z && l == a.dbg_layer) a.dbg_z[(tile * I8_M + row) * 64 + cq * 16 + j] = z;
-                        act[j] = tansig_scaled(z, tab);
+                        for (int j = 0; j < 8; ++j) {
+                            // value = accH * 2^32 + accL (exact integers, pre-biased so that the bit pattern is the
+                            // double 1.5 * 2^52 + acc), one rounding; z = -2 log2(e) * (W a + b)
+                            long long accH = I8_MAGIC52_BITS, accL = I8_MAGIC52_BITS;
+                            accH = (long long)(int)v0[j] * 65536ll + accH;
+                            accH = (long long)(int)v1[j] * 256ll + accH;
+                            accH = (long long)(int)v2[j] * 1ll + accH;
+                            accL = (long long)(int)v3[j] * 16777216ll + accL;
+                            accL = (long long)(int)v4[j] * 65536ll + accL;
+                            accL = (long long)(int)v5[j] * 256ll + accL;
+                            accL = (long long)(int)v6[j] * 1ll + accL;
+                            const double dl = __longlong_as_double(accL) - I8_MAGIC52;
+                            const double dh = __longlong_as_double(accH) - I8_MAGIC52;
+                            const double val = fma(dh, 4294967296.0, dl);
+                            const double2 cb = csbs[half * 8 + j];
+                            z[half * 8 + j] = fma(val, cb.x, cb.y);
+                        }
+                    }
+                    if (a.dbg_z && l == a.dbg_layer) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) a.dbg_z[(tile * I8_M + row) * 64 + cq * 16 + j] = z[j];
+                    }
+                    // Phase 2: tansig, four neurons at a time; the activations are re-sliced and stored as soon as two
+                    // groups (8 digit bytes per slice) are ready, or fed to the linear output layer
+                    uint8_t* abuf = sm + L::OFF_A + ln * I8_AH_BYTES + cq * (I8_M * 16) + row * 16;
+                    uint32_t keep[I8_NS];
+                    double part = 0.0;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        double zz[4], act[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) zz[i] = z[g * 4 + i];
+                        tansig_scaled_vec<4>(zz, act, tab);
+                        if (l < NHID - 1) {
+                            unsigned long long u[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) u[i] = i8_quantize(act[i], 2251799813685248.0 /* 2^51 */);
+                            uint32_t w[I8_NS];
+                            w[0] = i8_pack4<0>(u[0], u[1], u[2], u[3]);
+                            w[1] = i8_pack4<1>(u[0], u[1], u[2], u[3]);
+                            w[2] = i8_pack4<2>(u[0], u[1], u[2], u[3]);
+                            w[3] = i8_pack4<3>(u[0], u[1], u[2], u[3]);
+                            w[4] = i8_pack4<4>(u[0], u[1], u[2], u[3]);
+                            w[5] = i8_pack4<5>(u[0], u[1], u[2], u[3]);
+                            w[6] = i8_pack4<6>(u[0], u[1], u[2], u[3]);
+                            if ((g & 1) == 0) {
+#pragma unroll
+                                for (int b = 0; b < I8_NS; ++b) keep[b] = w[b];
+                            } else {
+#pragma unroll
+                                for (int b = 0; b < I8_NS; ++b)
+                                    *reinterpret_cast<uint2*>(abuf + (6 - b) * (I8_M * 64) + (g >> 1) * 8) = make_uint2(keep[b], w[b]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) part = fma(wout[g * 4 + i], act[i], part);
+                        }
                     }
                     if (l < NHID - 1) {
-                        unsigned long long u[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) u[j] = i8_quantize(act[j], 2251799813685248.0 /* 2^51 */);
-                        uint8_t* abuf = sm + L::OFF_A + ln * I8_AH_BYTES + cq * (I8_M * 16) + row * 16;
-#define I8_STORE_SLICE(B)                                                                                              \
-    *reinterpret_cast<uint4*>(abuf + (6 - B) * (I8_M * 64)) =                                                          \
-        make_uint4(i8_pack4<B>(u[0], u[1], u[2], u[3]), i8_pack4<B>(u[4], u[5], u[6], u[7]),                           \
-                   i8_pack4<B>(u[8], u[9], u[10], u[11]), i8_pack4<B>(u[12], u[13], u[14], u[15]));
-                        I8_STORE_SLICE(0) I8_STORE_SLICE(1) I8_STORE_SLICE(2) I8_STORE_SLICE(3)
-                        I8_STORE_SLICE(4) I8_STORE_SLICE(5) I8_STORE_SLICE(6)
-#undef I8_STORE_SLICE
                         fence_async_smem();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(B_ACT + 8 * ln);
                     } else {
                         // linear output layer (neural_net_3D.m:61-65, 81-85): partial dot products per column quarter
-                        const double* wout = par + L::P_WOUT + cq * 16;
-                        double part = 0.0;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) part = fma(wout[j], act[j], part);
                         double* yp = reinterpret_cast<double*>(sm + L::OFF_A + ln * I8_AH_BYTES + I8_A0_BYTES);
                         yp[cq * I8_M + row] = part;
                         __syncwarp();
@@ -518,6 +677,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                             }
                         }
                     }
+                    I8_STAMP(step, 3);
+                    ++step;
                 }
     }
     tc_fence_before();
