@@ -170,7 +170,8 @@ static bool pack_fragments(const double* blob, i64 len, std::vector<double>& out
 }
 
 // ---------------------------------------------------------------------------------------------------
-// NN weights: blob -> int8 digit images (UMMA canonical K-major layout) + FP64 parameter block for k_mlp_i8.
+// NN weights: blob -> int8 digit images (UMMA canonical K-major layout, [k chunk][slice][neuron][16 B]) + FP64
+// parameter block for k_mlp_i8.
 // Row j of a layer is scaled by 2^e >= max|W[j,:]|, rounded to 54 fractional bits and written as 7 balanced
 // base-256 digits (slice 0 = most significant).  oracle/nn_i8_model.py states the same arithmetic.
 // ---------------------------------------------------------------------------------------------------
@@ -206,7 +207,7 @@ static void pack_i8(const double* blob, std::vector<uint8_t>& out)
                 const unsigned long long u = (unsigned long long)(wint + 0x0080808080808080ll);
                 for (int b = 0; b < I8_NS; ++b) {
                     const int digit = (int)((u >> (8 * b)) & 0xFF) - 128;
-                    img[(6 - b) * (I8_N * K) + (k / 16) * (I8_N * 16) + j * 16 + (k % 16)] = (uint8_t)(int8_t)digit;
+                    img[(k / 16) * (I8_NS * I8_N * 16) + (6 - b) * (I8_N * 16) + j * 16 + (k % 16)] = (uint8_t)(int8_t)digit;
                 }
             }
             // z = -2 log2(e) * (W a + b);  W a = 2^(e - 54) * 2^-ea * 2^48 * (sum of the kept digit-pair diagonals)

@@ -18,8 +18,9 @@
 //
 // Pipeline per CTA (one per SM, persistent over a contiguous range of 128-candidate tiles, two tiles in flight):
 //   warp 17      : TMA producer  -- cp.async.bulk of the layer-0 digit image of a tile (written by k_prep_i8)
-//   warp 16      : MMA issuer    -- one thread issues the 28 digit-pair tcgen05.mma chains of a layer into 7 TMEM
-//                                   accumulators (one per diagonal, 64 columns each), one commit per layer
+//   warp 16      : MMA issuer    -- one thread issues the 28 digit-pair products of a layer as 10 tcgen05.mma per k
+//                                   step (N up to 256: one A slice against up to four stacked weight slices) into 7
+//                                   TMEM accumulators (one per diagonal, 64 columns each), one commit per layer
 //   warps 0..15  : epilogue      -- tcgen05.ld a diagonal, int64 accumulate, DFMA + tansig, re-slice the activations
 //                                   into the next layer's A operand in shared memory (UMMA canonical K-major layout)
 //   While the epilogue warps work on tile X, the tensor core runs the next layer of tile Y.
@@ -44,10 +45,12 @@ constexpr int I8_EPI_WARPS = 16;
 constexpr int I8_THREADS = (I8_EPI_WARPS + 2) * 32;       // 576
 constexpr int I8_NBAR = 2 * I8_SLOTS + 8;                 // slot_full[8] slot_empty[8] a0_full[2] lane_free[2] act_ready[2] y_ready[2]
 
-// instruction descriptor: D = S32, B = signed int8, A = signed (top slice) or unsigned int8, both K-major, N = 64,
-// M = 128 (cute::UMMA::InstrDescriptor)
-constexpr uint32_t I8_IDESC_U = (2u << 4) | (0u << 7) | (1u << 10) | ((I8_N >> 3) << 17) | ((I8_M >> 4) << 24);
-constexpr uint32_t I8_IDESC_S = I8_IDESC_U | (1u << 7);
+// instruction descriptor: D = S32, B = signed int8, A = unsigned int8 (bit 7 set: signed, for the top slice), both
+// K-major, M = 128, N = n (cute::UMMA::InstrDescriptor)
+__host__ __device__ constexpr uint32_t i8_idesc(int n)
+{
+    return (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(I8_M >> 4) << 24);
+}
 
 // fixed-point constants
 #define I8_MAGIC52 6755399441055744.0                     /* 1.5 * 2^52 */
@@ -516,27 +519,29 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                     I8_STAMP(step, 2);
                     tc_fence_after();
                     if (elect_one()) {
-                        // A: 8 x 16 B core matrices, K chunks 2048 B apart (128 rows x 16 B), 8-row groups 128 B apart
-                        // W: K chunks 1024 B apart (64 rows x 16 B)
-                        const uint64_t ad0 = umma_desc(smem_u32(sm + L::OFF_A + ln * I8_AH_BYTES), I8_M * 16, 128);
-                        const uint64_t bd0 = umma_desc(smem_u32(sm + (l == 0 ? 0 : I8_W0_BYTES + (l - 1) * I8_WH_BYTES)), I8_N * 16, 128);
-                        if (l == 0) {
+                        // A image: [slice s][k chunk][128 rows][16 B]  -> LBO (between the two k chunks of one MMA) 2048
+                        // W image: [k chunk][slice t][64 rows][16 B]   -> LBO 7 * 1024; the slices t = ta..tb of one k
+                        //          chunk are 64 (tb - ta + 1) consecutive rows: ONE MMA of N = 64 (tb - ta + 1) forms
+                        //          the products of A slice s with all of them and lands them in the adjacent
+                        //          accumulators of the diagonals s + ta .. s + tb.  10 MMAs per k step instead of 28,
+                        //          and the A operand is read 10 times instead of 28.
+                        const uint32_t a_base = smem_u32(sm + L::OFF_A + ln * I8_AH_BYTES);
+                        const uint32_t w_base = smem_u32(sm + (l == 0 ? 0 : I8_W0_BYTES + (l - 1) * I8_WH_BYTES));
+                        const uint32_t a_slice = (l == 0) ? I8_M * I8_K0 : I8_M * 64;
+                        const int ksteps = (l == 0) ? 1 : 2;
+                        for (int kk = 0; kk < ksteps; ++kk) {
+                            const uint64_t bd0 = umma_desc(w_base + kk * 2 * (I8_NS * I8_N * 16), I8_NS * I8_N * 16, 128);
 #pragma unroll
-                            for (int d = 0; d < I8_ND; ++d)
-#pragma unroll
-                                for (int sd = 0; sd <= d; ++sd)
-                                    umma_i8(tmem + d * I8_N, ad0 + (uint64_t)((sd * (I8_M * I8_K0)) >> 4),
-                                            bd0 + (uint64_t)(((d - sd) * (I8_N * I8_K0)) >> 4), sd ? I8_IDESC_U : I8_IDESC_S, sd > 0);
-                        } else {
-#pragma unroll
-                            for (int d = 0; d < I8_ND; ++d)
-#pragma unroll
-                                for (int sd = 0; sd <= d; ++sd)
-#pragma unroll
-                                    for (int kk = 0; kk < 2; ++kk)
-                                        umma_i8(tmem + d * I8_N, ad0 + (uint64_t)((sd * (I8_M * 64) + kk * 2 * (I8_M * 16)) >> 4),
-                                                bd0 + (uint64_t)(((d - sd) * (I8_N * 64) + kk * 2 * (I8_N * 16)) >> 4),
-                                                sd ? I8_IDESC_U : I8_IDESC_S, (sd | kk) > 0);
+                            for (int sd = 0; sd < I8_NS; ++sd) {
+                                const uint64_t ad = umma_desc(a_base + sd * a_slice + kk * 2 * (I8_M * 16), I8_M * 16, 128);
+                                constexpr uint32_t SGN = 1u << 7;
+                                const int nt = I8_NS - sd;                 // weight slices t = 0 .. 6 - sd
+                                const int n0 = nt < 4 ? nt : 4;
+                                umma_i8(tmem + sd * I8_N, ad, bd0, i8_idesc(64 * n0) | (sd ? 0u : SGN), (sd | kk) > 0);
+                                if (nt > 4)
+                                    umma_i8(tmem + (sd + 4) * I8_N, ad, bd0 + (uint64_t)((4 * I8_N * 16) >> 4),
+                                            i8_idesc(64 * (nt - 4)) | (sd ? 0u : SGN), (sd | kk) > 0);
+                            }
                         }
                         umma_commit(B_FULL);
                         if (l == NHID - 1) umma_commit(B_FREE + 8 * ln);
