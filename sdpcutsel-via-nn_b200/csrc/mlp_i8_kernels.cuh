@@ -666,7 +666,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                         yp[cq * I8_M + row] = part;
                         __syncwarp();
                         if (lane == 0) mbar_arrive(B_Y + 8 * ln);
-                        if (cq == 0) {
+                        if (cq == ((2 * (int)p + ln) & 3)) {   // the finalising role rotates: no warp falls systematically behind
                             ok = mbar_wait(B_Y + 8 * ln, (uint32_t)p & 1, abort_flag, a.status);
                             ok = __all_sync(0xffffffffu, ok);
                             if (!ok) break;
