@@ -97,6 +97,17 @@ int sdpcs_set_cover_all(sdpcs_ctx *ctx, int rho, int64_t rank_begin, int64_t ran
  * agg_idx = agg_offset + i. */
 int sdpcs_set_cover_list(sdpcs_ctx *ctx, int rho, const int16_t *idx, int64_t N, int64_t agg_offset);
 
+/* Candidate set = pattern-E vertex cover P^E_rho built ON THE DEVICE from the sparsity pattern: every rho-clique of
+ * the off-diagonal graph of adj (n x n, non-zero = edge, either triangle) plus every smaller clique (size >= 2)
+ * contained in no clique one size larger, in the order of the reference's nested loops = lexicographic tuple order.
+ * Replaces cut_select_qp.py:401-449 (rho = 3), 457-483 (rho = 4), 485-522 (rho = 5).  Candidate i has
+ * agg_idx = agg_offset + i; *out_N (may be NULL) receives the number of candidates. */
+int sdpcs_set_cover_pattern(sdpcs_ctx *ctx, int rho, const uint8_t *adj, int64_t agg_offset, int64_t *out_N);
+
+/* The current list cover (sdpcs_set_cover_list / sdpcs_set_cover_pattern) as N x rho int16 rows padded with -1, in
+ * candidate order: the index tuples the reference keeps in agg_list[i][0] (cut_select_qp.py:525-540). */
+int sdpcs_get_cover_rows(sdpcs_ctx *ctx, int16_t *out_idx, int64_t cap_rows);
+
 int sdpcs_num_candidates(const sdpcs_ctx *ctx, int64_t *N);
 
 /* Score every candidate of the cover at the LP point vars_values = [X upper-tri row-major | x]

@@ -20,6 +20,7 @@ EXPORTS = [
     "sdpcs_num_candidates", "sdpcs_score", "sdpcs_scores", "sdpcs_counts", "sdpcs_topk", "sdpcs_merge_topk",
     "sdpcs_select", "sdpcs_unrank", "sdpcs_binom", "sdpcs_gen_cuts", "sdpcs_eigendecomp", "sdpcs_set_tri_pattern",
     "sdpcs_triangles", "sdpcs_nn_eval", "sdpcs_nn_debug_layer", "sdpcs_fp64_peak",
+    "sdpcs_set_cover_pattern", "sdpcs_get_cover_rows",
 ]
 
 NN_TCGEN05, NN_DMMA = 0, 1
@@ -131,6 +132,22 @@ class Engine(object):
         idx = np.ascontiguousarray(idx, dtype=np.int16).reshape(-1, rho)
         self._ck(self._lib.sdpcs_set_cover_list(self._ctx, c_int(rho), _ptr(idx), c_i64(idx.shape[0]), c_i64(agg_offset)))
         self.rho = rho
+
+    def set_cover_pattern(self, rho, adj, agg_offset=0):
+        """P^E_rho built on the device from the n x n sparsity pattern (cut_select_qp.py:401-522); returns N."""
+        adj = np.ascontiguousarray(np.asarray(adj) != 0, dtype=np.uint8)
+        if adj.shape != (self.n, self.n):
+            raise SdpcsError("adjacency must be n x n")
+        N = c_i64()
+        self._ck(self._lib.sdpcs_set_cover_pattern(self._ctx, c_int(rho), _ptr(adj), c_i64(agg_offset), ctypes.byref(N)))
+        self.rho = rho
+        return N.value
+
+    def cover_rows(self):
+        """The current list cover as (N, rho) int16 rows padded with -1 (agg_list[i][0] of the reference)."""
+        out = np.empty((self.num_candidates, self.rho), dtype=np.int16)
+        self._ck(self._lib.sdpcs_get_cover_rows(self._ctx, _ptr(out), c_i64(out.shape[0])))
+        return out
 
     @property
     def num_candidates(self):

@@ -9,6 +9,7 @@
 
 #include "../../include/sdpcutsel.h"
 #include "aux_kernels.cuh"
+#include "cover_kernels.cuh"
 #include "score_kernels.cuh"
 #include "mlp_i8_kernels.cuh"
 #include "select_kernels.cuh"
@@ -476,6 +477,111 @@ extern "C" int sdpcs_set_cover_list(sdpcs_ctx* ctx, int rho, const int16_t* idx,
     int rc = alloc_scores(ctx, N);
     if (rc) return rc;
     ctx->rho = rho; ctx->mode = 2; ctx->base = agg_offset; ctx->N = N;
+    return SDPCS_OK;
+}
+
+// P^E_rho built on the device (cover_kernels.cuh); replaces the nested loops of cut_select_qp.py:401-522.
+extern "C" int sdpcs_set_cover_pattern(sdpcs_ctx* ctx, int rho, const uint8_t* adj, int64_t agg_offset, int64_t* out_N)
+{
+    if (!ctx) return SDPCS_ERR_INVALID;
+    if (!ctx->n) return ctx->fail(SDPCS_ERR_STATE, "set_instance first");
+    if (rho < 2 || rho > 5 || !adj) return ctx->fail(SDPCS_ERR_INVALID, "bad pattern cover arguments");
+    const int n = ctx->n;
+    if (n > 256) return ctx->fail(SDPCS_ERR_INVALID, "pattern cover needs n <= 256");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->mode = 0; ctx->have = 0; ctx->N = 0;
+    std::vector<Mask256> masks(n);
+    std::vector<int> edges;
+    for (int i = 0; i < n; ++i) {
+        for (int w = 0; w < 4; ++w) masks[i].w[w] = 0;
+        for (int j = 0; j < n; ++j)
+            if (j != i && (adj[(size_t)i * n + j] || adj[(size_t)j * n + i])) masks[i].w[j >> 6] |= 1ull << (j & 63);
+    }
+    for (int i = 0; i < n; ++i)
+        for (int j = i + 1; j < n; ++j)
+            if (masks[i].w[j >> 6] >> (j & 63) & 1) { edges.push_back(i); edges.push_back(j); }
+    const i64 E = (i64)edges.size() / 2;
+    for (int d = 2; d <= 5; ++d) {
+        if (ctx->d_idx[d]) { cudaFree(ctx->d_idx[d]); ctx->d_idx[d] = nullptr; }
+        if (ctx->d_pos[d]) { cudaFree(ctx->d_pos[d]); ctx->d_pos[d] = nullptr; }
+        ctx->Nd[d] = 0;
+    }
+    i64 N = 0;
+    if (E > 0) {
+        // scratch: masks | edges | counts | pos_off | cls_off
+        const size_t o_edges = sizeof(Mask256) * n, o_counts = o_edges + sizeof(int) * 2 * E, o_pos = (o_counts + sizeof(int) * 4 * E + 7) & ~(size_t)7,
+                     o_cls = o_pos + sizeof(i64) * E, total = o_cls + sizeof(i64) * 4 * E;
+        int rc = ensure_scratch(ctx, total);
+        if (rc) return rc;
+        uint8_t* sc = static_cast<uint8_t*>(ctx->d_scratch);
+        CU(cudaMemcpyAsync(sc, masks.data(), sizeof(Mask256) * n, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(sc + o_edges, edges.data(), sizeof(int) * 2 * E, cudaMemcpyHostToDevice, ctx->stream));
+        CoverArgs a;
+        memset(&a, 0, sizeof(a));
+        a.n = n; a.rho = rho; a.adj = reinterpret_cast<const Mask256*>(sc); a.edges = reinterpret_cast<const int*>(sc + o_edges); a.E = E;
+        a.counts = reinterpret_cast<int*>(sc + o_counts);
+        const unsigned grid = (unsigned)((E + 127) / 128);
+        k_cover_pattern<false><<<grid, 128, 0, ctx->stream>>>(a);
+        CU(cudaGetLastError());
+        std::vector<int> counts(4 * E);
+        CU(cudaMemcpyAsync(counts.data(), a.counts, sizeof(int) * 4 * E, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        std::vector<i64> pos_off(E), cls_off(4 * E);
+        i64 tot[4] = {0, 0, 0, 0};
+        for (i64 e = 0; e < E; ++e) {
+            pos_off[e] = N;
+            for (int d = 0; d < 4; ++d) { cls_off[4 * e + d] = tot[d]; tot[d] += counts[4 * e + d]; N += counts[4 * e + d]; }
+        }
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        size_t need = 0;
+        for (int d = 2; d <= 5; ++d) need += (size_t)tot[d - 2] * (d + sizeof(i64));
+        if (need + (size_t)N * 32 > free_b)
+            return ctx->fail(SDPCS_ERR_NOMEM, "pattern cover of " + std::to_string(N) + " candidates does not fit on the device");
+        for (int d = 2; d <= 5; ++d) {
+            ctx->Nd[d] = tot[d - 2];
+            if (!ctx->Nd[d]) continue;
+            CU(cudaMalloc(&ctx->d_idx[d], (size_t)ctx->Nd[d] * d));
+            CU(cudaMalloc(&ctx->d_pos[d], (size_t)ctx->Nd[d] * sizeof(i64)));
+            a.idx[d] = ctx->d_idx[d]; a.pos[d] = ctx->d_pos[d];
+        }
+        CU(cudaMemcpyAsync(sc + o_pos, pos_off.data(), sizeof(i64) * E, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(sc + o_cls, cls_off.data(), sizeof(i64) * 4 * E, cudaMemcpyHostToDevice, ctx->stream));
+        a.pos_off = reinterpret_cast<const i64*>(sc + o_pos); a.cls_off = reinterpret_cast<const i64*>(sc + o_cls);
+        k_cover_pattern<true><<<grid, 128, 0, ctx->stream>>>(a);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(ctx->stream));   // the host vectors above go out of scope
+    }
+    if (ctx->d_lam && ctx->score_cap < N) { cudaFree(ctx->d_lam); cudaFree(ctx->d_obj); ctx->d_lam = ctx->d_obj = nullptr; ctx->score_cap = 0; }
+    int rc = alloc_scores(ctx, N);
+    if (rc) return rc;
+    ctx->rho = rho; ctx->mode = 2; ctx->base = agg_offset; ctx->N = N;
+    if (out_N) *out_N = N;
+    return SDPCS_OK;
+}
+
+// The list cover as N x rho int16 rows (padded with -1), in candidate order: what the reference keeps as
+// agg_list[i][0] (cut_select_qp.py:525-540).
+extern "C" int sdpcs_get_cover_rows(sdpcs_ctx* ctx, int16_t* out_idx, int64_t cap_rows)
+{
+    if (!ctx) return SDPCS_ERR_INVALID;
+    if (ctx->mode != 2) return ctx->fail(SDPCS_ERR_STATE, "no list cover set");
+    if (cap_rows < ctx->N || (ctx->N > 0 && !out_idx)) return ctx->fail(SDPCS_ERR_INVALID, "output buffer too small");
+    if (!ctx->N) return SDPCS_OK;
+    CU(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)ctx->N * ctx->rho * sizeof(int16_t);
+    int rc = ensure_scratch(ctx, bytes);
+    if (rc) return rc;
+    int16_t* d_rows = static_cast<int16_t*>(ctx->d_scratch);
+    for (int d = 2; d <= ctx->rho; ++d) {
+        if (!ctx->Nd[d]) continue;
+        const unsigned grid = (unsigned)std::min<i64>((ctx->Nd[d] + 255) / 256, (i64)ctx->sms * 8);
+        k_cover_rows<<<grid, 256, 0, ctx->stream>>>(ctx->d_idx[d], ctx->d_pos[d], ctx->Nd[d], d, ctx->rho, d_rows);
+        CU(cudaGetLastError());
+    }
+    CU(cudaMemcpyAsync(out_idx, d_rows, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return SDPCS_OK;
 }
 

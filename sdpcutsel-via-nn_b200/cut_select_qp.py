@@ -136,7 +136,12 @@ class B200CutSelection(object):
             if _is_complete(adj):      # dense pattern: P^E_dim is all subsets in lex order -> nothing to store
                 agg = cover.AggList(n, dim, Q_arr, n_all=_capi.binom(n, dim))
             else:
-                agg = cover.AggList(n, dim, Q_arr, idx=cover.pattern_E(adj, dim))
+                # the nested clique loops (cut_select_qp.py:401-522) run on the device; the index tuples come back once
+                # for the lazy agg_list view, the device context stays attached as the cover's engine
+                eng = self._new_engine()
+                eng.set_cover_pattern(dim, adj)
+                agg = cover.AggList(n, dim, Q_arr, idx=eng.cover_rows())
+                agg._engine = eng
         if len(agg) >= self._THRES_MAX_SUBS:
             return len(agg)
         self._agg_list = agg
