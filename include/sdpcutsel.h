@@ -157,6 +157,20 @@ int sdpcs_binom(int n, int k, int64_t *out);
 int sdpcs_gen_cuts(sdpcs_ctx *ctx, int rho, const int16_t *sets, int64_t m, const double *vars_values,
                    int64_t *out_ind, double *out_val, double *out_rhs, double *out_lam, uint8_t *out_violated);
 
+/* Row emission in one shot.  The violated cuts of sdpcs_gen_cuts as CSR rows -- row starts
+ * out_rowptr[rows+1], LP columns out_ind, coefficients out_val (capacity m x width each), right-hand sides out_rhs[m],
+ * sense >= for every row: the arrays CPXaddrows takes, instead of one cplex.SparsePair per cut
+ * (cut_select_qp.py:747-754).  out_src[r] (may be NULL) = index into `sets` of row r; *out_nrows = #rows. */
+int sdpcs_gen_cuts_csr(sdpcs_ctx *ctx, int rho, const int16_t *sets, int64_t m, const double *vars_values,
+                       int64_t *out_rowptr, int64_t *out_ind, double *out_val, double *out_rhs, int64_t *out_src,
+                       int64_t *out_nrows);
+
+/* Triangle-inequality rows (cut_select_qp.py:846-860) for m (triple lex rank, type) pairs as returned by
+ * sdpcs_triangles, as CSR: 4 entries per row for types 0..2 (rhs 0), 6 for type 3 (rhs -1), sense >=.
+ * Host utility (no GPU): out_rowptr[m+1], out_ind / out_val capacity 6 m, out_rhs[m]. */
+int sdpcs_triangle_rows_csr(int n, const int64_t *triple_rank, const int8_t *type, int64_t m, int64_t *out_rowptr,
+                            int64_t *out_ind, double *out_val, double *out_rhs);
+
 /* Eigen-decomposition of one [1 x^T; x X] matrix of order d+1 (cut_select_qp.py:788-797): eigenvalues
  * ascending, eigenvectors as columns of V (row-major (d+1)x(d+1)); out_vecs may be NULL. */
 int sdpcs_eigendecomp(sdpcs_ctx *ctx, int d, const double *curr_pt, const double *X_slice,

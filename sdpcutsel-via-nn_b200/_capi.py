@@ -20,7 +20,7 @@ EXPORTS = [
     "sdpcs_num_candidates", "sdpcs_score", "sdpcs_scores", "sdpcs_counts", "sdpcs_topk", "sdpcs_merge_topk",
     "sdpcs_select", "sdpcs_unrank", "sdpcs_binom", "sdpcs_gen_cuts", "sdpcs_eigendecomp", "sdpcs_set_tri_pattern",
     "sdpcs_triangles", "sdpcs_nn_eval", "sdpcs_nn_debug_layer", "sdpcs_fp64_peak",
-    "sdpcs_set_cover_pattern", "sdpcs_get_cover_rows",
+    "sdpcs_set_cover_pattern", "sdpcs_get_cover_rows", "sdpcs_gen_cuts_csr", "sdpcs_triangle_rows_csr",
 ]
 
 NN_TCGEN05, NN_DMMA = 0, 1
@@ -230,6 +230,20 @@ class Engine(object):
                                           _ptr(lam), _ptr(viol)))
         return ind, val, rhs, lam, viol.astype(bool)
 
+    def gen_cuts_csr(self, rho, sets, vars_values):
+        """Violated eigenvector cuts as CSR rows: dict(rowptr, ind, val, rhs, src); sense >= for every row."""
+        sets = np.ascontiguousarray(sets, dtype=np.int16).reshape(-1, rho)
+        m = sets.shape[0]
+        width = rho + rho * (rho + 1) // 2
+        rowptr, ind, val = np.zeros(m + 1, np.int64), np.empty(m * width, np.int64), np.empty(m * width)
+        rhs, src, nrows = np.empty(m), np.empty(m, np.int64), c_i64()
+        v = _f64(vars_values)
+        self._ck(self._lib.sdpcs_gen_cuts_csr(self._ctx, c_int(rho), _ptr(sets), c_i64(m), _ptr(v), _ptr(rowptr), _ptr(ind), _ptr(val),
+                                              _ptr(rhs), _ptr(src), ctypes.byref(nrows)))
+        r = nrows.value
+        nnz = int(rowptr[r])
+        return dict(rowptr=rowptr[:r + 1], ind=ind[:nnz], val=val[:nnz], rhs=rhs[:r], src=src[:r])
+
     def eigendecomp(self, d, curr_pt, X_slice, want_vecs=True):
         pt, Xs = _f64(curr_pt), _f64(X_slice)
         vals = np.empty(d + 1)
@@ -268,6 +282,20 @@ class Engine(object):
         a, b = c_dbl(), c_dbl()
         self._ck(self._lib.sdpcs_fp64_peak(self._ctx, ctypes.byref(a), ctypes.byref(b)))
         return dict(dfma_tflops=a.value, dmma_tflops=b.value)
+
+
+def triangle_rows_csr(n, triple_rank, types):
+    """CSR rows of the triangle inequalities (cut_select_qp.py:846-860): dict(rowptr, ind, val, rhs)."""
+    lib = load_library()
+    rank = np.ascontiguousarray(triple_rank, dtype=np.int64).ravel()
+    typ = np.ascontiguousarray(types, dtype=np.int8).ravel()
+    m = rank.size
+    rowptr, ind, val, rhs = np.zeros(m + 1, np.int64), np.empty(6 * m, np.int64), np.empty(6 * m), np.empty(m)
+    rc = lib.sdpcs_triangle_rows_csr(c_int(n), _ptr(rank), _ptr(typ), c_i64(m), _ptr(rowptr), _ptr(ind), _ptr(val), _ptr(rhs))
+    if rc != 0:
+        raise SdpcsError("sdpcs_triangle_rows_csr failed (%d)" % rc)
+    nnz = int(rowptr[m])
+    return dict(rowptr=rowptr, ind=ind[:nnz], val=val[:nnz], rhs=rhs)
 
 
 def unrank(n, rho, ranks):

@@ -1043,6 +1043,76 @@ extern "C" int sdpcs_gen_cuts(sdpcs_ctx* ctx, int rho, const int16_t* sets, int6
     return SDPCS_OK;
 }
 
+// The violated eigenvector cuts of sdpcs_gen_cuts as CSR rows (the layout CPXaddrows takes: row starts, column
+// indices, values, right-hand sides; sense >= for all), in one shot instead of one SparsePair object per cut
+// (cut_select_qp.py:747-754).  out_src[r] = index into `sets` of emitted row r.
+extern "C" int sdpcs_gen_cuts_csr(sdpcs_ctx* ctx, int rho, const int16_t* sets, int64_t m, const double* vars_values,
+                                  int64_t* out_rowptr, int64_t* out_ind, double* out_val, double* out_rhs, int64_t* out_src,
+                                  int64_t* out_nrows)
+{
+    if (!ctx || m < 0 || rho < 2 || rho > 5 || !out_rowptr || !out_nrows) return SDPCS_ERR_INVALID;
+    *out_nrows = 0;
+    out_rowptr[0] = 0;
+    if (m == 0) return SDPCS_OK;
+    if (!out_ind || !out_val || !out_rhs) return ctx->fail(SDPCS_ERR_INVALID, "null pointer");
+    const int width = rho + rho * (rho + 1) / 2;
+    std::vector<int64_t> ind((size_t)m * width);
+    std::vector<double> val((size_t)m * width), rhs(m), lam(m);
+    std::vector<uint8_t> viol(m);
+    int rc = sdpcs_gen_cuts(ctx, rho, sets, m, vars_values, ind.data(), val.data(), rhs.data(), lam.data(), viol.data());
+    if (rc) return rc;
+    i64 rows = 0, nnz = 0;
+    for (i64 i = 0; i < m; ++i) {
+        if (!viol[i]) continue;                                   // eigvals[0] >= _THRES_NEG_EIGVAL: no cut (cut_select_qp.py:743)
+        for (int t = 0; t < width; ++t) {
+            if (ind[i * width + t] < 0) break;                    // rows of cliques smaller than rho are -1 padded
+            out_ind[nnz] = ind[i * width + t];
+            out_val[nnz] = val[i * width + t];
+            ++nnz;
+        }
+        out_rhs[rows] = rhs[i];
+        if (out_src) out_src[rows] = i;
+        out_rowptr[++rows] = nnz;
+    }
+    *out_nrows = rows;
+    return SDPCS_OK;
+}
+
+// Triangle-inequality rows (cut_select_qp.py:846-860) for (triple rank, type) pairs as CSR; host utility.
+extern "C" int sdpcs_triangle_rows_csr(int n, const int64_t* triple_rank, const int8_t* type, int64_t m, int64_t* out_rowptr,
+                                       int64_t* out_ind, double* out_val, double* out_rhs)
+{
+    if (n < 3 || n > 65535 || m < 0 || !out_rowptr) return SDPCS_ERR_INVALID;
+    out_rowptr[0] = 0;
+    if (m == 0) return SDPCS_OK;
+    if (!triple_rank || !type || !out_ind || !out_val || !out_rhs) return SDPCS_ERR_INVALID;
+    const i64 T = (i64)binom_small(n, 3), nb_lifted = (i64)n * (n + 1) / 2;
+    static const double COEF[4][6] = {{-1, -1, 1, 1, 0, 0}, {-1, 1, -1, 1, 0, 0}, {1, -1, -1, 1, 0, 0}, {1, 1, 1, -1, -1, -1}};
+    i64 nnz = 0;
+    for (i64 r = 0; r < m; ++r) {
+        if (triple_rank[r] < 0 || triple_rank[r] >= T || type[r] < 0 || type[r] > 3) return SDPCS_ERR_INVALID;
+        int c[3];
+        lex_unrank<3>(n, (u64)triple_rank[r], c);
+        const i64 i1 = c[0], i2 = c[1], i3 = c[2];
+        out_ind[nnz] = n * i1 - i1 * (i1 + 1) / 2 + i2;
+        out_ind[nnz + 1] = n * i1 - i1 * (i1 + 1) / 2 + i3;
+        out_ind[nnz + 2] = n * i2 - i2 * (i2 + 1) / 2 + i3;
+        const int t = type[r];
+        int w = 4;
+        if (t == 3) {
+            out_ind[nnz + 3] = i1 + nb_lifted; out_ind[nnz + 4] = i2 + nb_lifted; out_ind[nnz + 5] = i3 + nb_lifted;
+            w = 6;
+        } else {
+            out_ind[nnz + 3] = c[t] + nb_lifted;
+        }
+        for (int q = 0; q < w; ++q) out_val[nnz + q] = COEF[t][q];
+        out_rhs[r] = (t == 3) ? -1.0 : 0.0;
+        nnz += w;
+        out_rowptr[r + 1] = nnz;
+    }
+    return SDPCS_OK;
+}
+
 extern "C" int sdpcs_eigendecomp(sdpcs_ctx* ctx, int d, const double* curr_pt, const double* X_slice, double* out_vals,
                                  double* out_vecs)
 {

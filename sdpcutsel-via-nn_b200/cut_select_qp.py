@@ -214,13 +214,11 @@ class B200CutSelection(object):
             for i, s in enumerate(sets):
                 packed[i, :len(s)] = s
             eng = self._engine_for(self._agg_list) if isinstance(self._agg_list, cover.AggList) else self._new_engine()
-            ind, val, rhs, lam, viol = eng.gen_cuts(dim, packed, vars_values)
-            for i, s in enumerate(sets):
-                if viol[i]:                                                        # eigvals[0] < _THRES_NEG_EIGVAL
-                    w = len(s) + len(s) * (len(s) + 1) // 2
-                    coeffs_sdp.append(SparsePair(ind=[int(v) for v in ind[i, :w]], val=[float(v) for v in val[i, :w]]))
-                    rhs_sdp.append(float(rhs[i]))
-                    senses_sdp.append("G")
+            csr = eng.gen_cuts_csr(dim, packed, vars_values)       # violated cuts only (eigvals[0] < _THRES_NEG_EIGVAL)
+            if _add_rows_csr(my_prob, csr):
+                return len(csr["rhs"])
+            coeffs_sdp, rhs_sdp = _sparse_pairs(csr), csr["rhs"].tolist()
+            senses_sdp = ["G"] * len(rhs_sdp)
         my_prob.linear_constraints.add(lin_expr=coeffs_sdp, rhs=rhs_sdp, senses=senses_sdp)
         return len(rhs_sdp)
 
@@ -247,21 +245,30 @@ class B200CutSelection(object):
                           min(self._TRI_CUTS_PER_ROUND_MAX, V))                    # cut_select_qp.py:843-844
         if nb_tri_cuts > V:
             raise IndexError("list index out of range")                            # the reference indexes past the list here
-        triples = _capi.unrank(n, 3, t["rank"][:nb_tri_cuts]) if nb_tri_cuts else np.zeros((0, 3), np.int32)
-        dict_coeffs_tri = {0: [-1, -1, 1, 1], 1: [-1, 1, -1, 1], 2: [1, -1, -1, 1], 3: [1, 1, 1, -1, -1, -1]}
-        coeffs_tri, rhs_tri, senses_tri = [0] * nb_tri_cuts, [0] * nb_tri_cuts, ["G"] * nb_tri_cuts
-        for ix in range(nb_tri_cuts):
-            i1, i2, i3 = (int(v) for v in triples[ix])
-            typ = int(t["type"][ix])
-            x12, x13, x23 = n * i1 - i1 * (i1 + 1) // 2 + i2, n * i1 - i1 * (i1 + 1) // 2 + i3, n * i2 - i2 * (i2 + 1) // 2 + i3
-            if typ == 3:
-                coeffs_tri[ix] = SparsePair(ind=[x12, x13, x23, i1 + nb_lifted, i2 + nb_lifted, i3 + nb_lifted], val=dict_coeffs_tri[3])
-                rhs_tri[ix] = -1
-            else:
-                coeffs_tri[ix] = SparsePair(ind=[x12, x13, x23, (i1, i2, i3)[typ] + nb_lifted], val=dict_coeffs_tri[typ])
-                rhs_tri[ix] = 0
+        csr = _capi.triangle_rows_csr(n, t["rank"][:nb_tri_cuts], t["type"][:nb_tri_cuts])      # cut_select_qp.py:846-860
+        if _add_rows_csr(my_prob, csr):
+            return nb_tri_cuts
+        coeffs_tri, rhs_tri = _sparse_pairs(csr, as_int=True), [int(v) for v in csr["rhs"]]
+        senses_tri = ["G"] * nb_tri_cuts
         my_prob.linear_constraints.add(lin_expr=coeffs_tri, rhs=rhs_tri, senses=senses_tri)
         return nb_tri_cuts
+
+
+def _add_rows_csr(my_prob, csr):
+    """One-shot row emission: a sink that offers ``linear_constraints.add_rows_csr(rowptr, ind, val, rhs, senses)``
+    (e.g. a thin CPXaddrows wrapper) receives the CSR arrays as they come from the C ABI."""
+    add = getattr(my_prob.linear_constraints, "add_rows_csr", None)
+    if add is None:
+        return False
+    add(csr["rowptr"], csr["ind"], csr["val"], csr["rhs"], "G" * len(csr["rhs"]))
+    return True
+
+
+def _sparse_pairs(csr, as_int=False):
+    """CSR -> the reference's list of cplex.SparsePair (cut_select_qp.py:747, 849-858), sliced from two flat lists."""
+    ind, ptr = csr["ind"].tolist(), csr["rowptr"].tolist()
+    val = [int(v) for v in csr["val"]] if as_int else csr["val"].tolist()
+    return [SparsePair(ind=ind[a:b], val=val[a:b]) for a, b in zip(ptr[:-1], ptr[1:])]
 
 
 class _NNFunc(object):

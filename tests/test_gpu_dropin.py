@@ -166,3 +166,55 @@ def test_eigendecomp_and_nn_callables(golden, blobs):
         x = golden["nn%d_in" % d][20]
         input_arr[:] = x
         assert abs(func(input_arr) - golden["nn%d_out" % d][20]) < 1e-11
+
+
+class _CsrSink(object):
+    """A cut sink that takes rows in one shot (the shape of a CPXaddrows wrapper)."""
+
+    def __init__(self):
+        self.calls = []
+
+    def add_rows_csr(self, rowptr, ind, val, rhs, senses):
+        self.calls.append((np.array(rowptr), np.array(ind), np.array(val), np.array(rhs), senses))
+
+    def add(self, **kw):  # pragma: no cover - must not be used when add_rows_csr exists
+        raise AssertionError("per-row path used although the sink takes CSR")
+
+
+class _CsrProb(object):
+    def __init__(self):
+        self.linear_constraints = _CsrSink()
+
+
+def test_one_shot_csr_row_emission(golden):
+    """Same round as test_cfg2_rounds_and_triangles, but the cuts leave as CSR arrays: identical rows."""
+    n, Q_arr, adj = inst_arrays(golden, "spar125-075-1")
+    vv = golden["cfg2_vars"]
+    ref, csr = pkg.CutSolver(), pkg.CutSolver()
+    ref.set_instance(Q_arr, adj, n, dim=3)
+    csr.set_instance(Q_arr, adj, n, dim=3, my_prob=_CsrProb())
+    for cs in (ref, csr):
+        cs._load_neural_nets()
+        N = cs._get_sdp_vertex_cover(3)
+    k = min(int(np.floor(0.1 * N)), ref._SDP_CUTS_PER_ROUND_MAX)
+    for strat in (1, 2):
+        ref._my_prob.linear_constraints.rows = []
+        csr._my_prob.linear_constraints.calls = []
+        nb = [cs._gen_eigcuts_selected(strat, k, cs._sel_eigcut_by_ordering_on_measure(strat, vv, 1, sel_size=k), vars_values=vv)
+              for cs in (ref, csr)]
+        assert nb[0] == nb[1] == int(golden["cfg2_s%d_nbcuts" % strat])
+        (rowptr, ind, val, rhs, senses), = csr._my_prob.linear_constraints.calls
+        rows = rows_of(ref)
+        assert len(rows) == nb[0] == rhs.size == len(senses) and set(senses) == {"G"} and rowptr[0] == 0
+        for r, (sp, rh, _) in enumerate(rows):
+            a, b = rowptr[r], rowptr[r + 1]
+            assert ind[a:b].tolist() == sp.ind and val[a:b].tolist() == sp.val and rhs[r] == rh
+    ref._my_prob.linear_constraints.rows = []
+    csr._my_prob.linear_constraints.calls = []
+    for cs in (ref, csr):
+        cs._CutSolver__preprocess_triangle_ineq()
+        assert cs._CutSolver__separate_and_add_triangle(0.1, vv) == 10000
+    (rowptr, ind, val, rhs, senses), = csr._my_prob.linear_constraints.calls
+    for r, (sp, rh, _) in enumerate(rows_of(ref)):
+        a, b = rowptr[r], rowptr[r + 1]
+        assert ind[a:b].tolist() == sp.ind and val[a:b].tolist() == sp.val and rhs[r] == rh

@@ -66,3 +66,26 @@ def test_solver_surface_names():
         cs._sel_eigcut_by_ordering_on_measure(3, None, 1)
     with pytest.raises(NotImplementedError):
         cs._get_sdp_vertex_cover(3, ch_ext=1)
+
+
+def test_triangle_rows_csr_match_the_reference_rows():
+    """sdpcs_triangle_rows_csr (host utility of the C ABI) against the restated row assembly of
+    cut_select_qp.py:846-860 for every type, incl. ragged row lengths (4 / 6 entries) and m = 0."""
+    n = 23
+    rng = np.random.default_rng(3)
+    T = pkg._capi.binom(n, 3)
+    ranks = np.concatenate([[0, T - 1], rng.integers(0, T, 200)])
+    types = np.concatenate([[3, 0], rng.integers(0, 4, 200)]).astype(np.int8)
+    csr = pkg._capi.triangle_rows_csr(n, ranks, types)
+    triples = pkg._capi.unrank(n, 3, ranks)
+    assert csr["rowptr"][0] == 0 and csr["rowptr"][-1] == csr["ind"].size == csr["val"].size
+    for r in range(ranks.size):
+        ind, val, rhs = orc.triangle_row(n, tuple(int(v) for v in triples[r]), int(types[r]))
+        a, b = csr["rowptr"][r], csr["rowptr"][r + 1]
+        assert csr["ind"][a:b].tolist() == list(ind) and csr["val"][a:b].tolist() == list(val) and csr["rhs"][r] == rhs
+    empty = pkg._capi.triangle_rows_csr(n, [], [])
+    assert empty["rowptr"].tolist() == [0] and empty["ind"].size == 0
+    with pytest.raises(pkg._capi.SdpcsError):
+        pkg._capi.triangle_rows_csr(n, [T], [0])
+    with pytest.raises(pkg._capi.SdpcsError):
+        pkg._capi.triangle_rows_csr(n, [0], [4])
