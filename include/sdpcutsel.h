@@ -171,6 +171,16 @@ int sdpcs_gen_cuts_csr(sdpcs_ctx *ctx, int rho, const int16_t *sets, int64_t m, 
 int sdpcs_triangle_rows_csr(int n, const int64_t *triple_rank, const int8_t *type, int64_t m, int64_t *out_rowptr,
                             int64_t *out_ind, double *out_val, double *out_rhs);
 
+/* Dense eigenvalue cuts, strat 0 (CutSolver.__gen_dense_eigcuts, cut_select_qp.py:757-786): one
+ * eigen-decomposition of the full [1 x^T; x X] (order n + 1 <= 256) on the device; every eigenvalue among the n
+ * smallest below thres_neg_eigval gives one dense row of width n + n(n+1)/2 over the LP columns
+ * [nb_lifted + i, i < n | 0 .. nb_lifted) (x variables first, then X upper-triangular row-major):
+ * coefficients out_val (row-major, capacity max_cuts rows), right-hand side out_rhs = -v0^2, sense >=.
+ * out_eigvals (may be NULL): the n + 1 eigenvalues ascending.  *out_ncuts = number of rows; if it exceeds max_cuts
+ * the call fails with SDPCS_ERR_INVALID after setting *out_ncuts (max_cuts = n always suffices). */
+int sdpcs_dense_eigcuts(sdpcs_ctx *ctx, const double *vars_values, int64_t max_cuts, double *out_eigvals,
+                        int64_t *out_ncuts, double *out_val, double *out_rhs);
+
 /* Eigen-decomposition of one [1 x^T; x X] matrix of order d+1 (cut_select_qp.py:788-797): eigenvalues
  * ascending, eigenvectors as columns of V (row-major (d+1)x(d+1)); out_vecs may be NULL. */
 int sdpcs_eigendecomp(sdpcs_ctx *ctx, int d, const double *curr_pt, const double *X_slice,

@@ -490,3 +490,29 @@ def triangle_row(n, triple, typ):
 def sel_size_rule(sel, N):
     """cut_select_qp.py:123-125."""
     return min(int(np.floor(sel * N)) if sel < 1 else min(sel, N), SDP_CUTS_PER_ROUND_MAX)
+
+
+def dense_eigcuts(n, vars_values, thres=THRES_NEG_EIGVAL):
+    """Dense eigenvalue cuts (strat 0), cut_select_qp.py:757-786: one eigh of the full [1 x^T; x X] of order n + 1;
+    every eigenvalue among the n smallest that is below the threshold gives the row
+    [2 v0 v_i (on x_i) | v_i v_j (2 if i != j) (on X_ij, upper-triangular row-major)] >= -v0^2.
+    Returns (ind, val (ncuts, n + n(n+1)/2), rhs, eigvals)."""
+    nb_lifted = n * (n + 1) // 2
+    X_vals, x_vals = np.asarray(vars_values[:nb_lifted]), np.asarray(vars_values[nb_lifted:])
+    mat = np.zeros((n + 1, n + 1))
+    mat[0, 0] = 1
+    mat[0, 1:] = x_vals
+    iu = np.triu_indices(n)
+    mat[iu[0] + 1, iu[1] + 1] = X_vals
+    eigvals, evecs = np.linalg.eigh(mat, "U")
+    ind = np.array([i + nb_lifted for i in range(n)] + list(range(nb_lifted)), dtype=np.int64)
+    i1, i2 = np.triu_indices(n + 1)
+    keep = i2 >= 1                                     # idx2 runs from max(idx1, 1)
+    i1, i2 = i1[keep], i2[keep]
+    vals, rhs = [], []
+    for ix in range(n):
+        if eigvals[ix] < thres:
+            v = evecs[:, ix]
+            vals.append(v[i1] * v[i2] * np.where(i1 != i2, 2.0, 1.0))
+            rhs.append(-v[0] * v[0])
+    return ind, np.array(vals).reshape(len(rhs), n + nb_lifted), np.array(rhs), eigvals

@@ -20,7 +20,7 @@ EXPORTS = [
     "sdpcs_num_candidates", "sdpcs_score", "sdpcs_scores", "sdpcs_counts", "sdpcs_topk", "sdpcs_merge_topk",
     "sdpcs_select", "sdpcs_unrank", "sdpcs_binom", "sdpcs_gen_cuts", "sdpcs_eigendecomp", "sdpcs_set_tri_pattern",
     "sdpcs_triangles", "sdpcs_nn_eval", "sdpcs_nn_debug_layer", "sdpcs_fp64_peak",
-    "sdpcs_set_cover_pattern", "sdpcs_get_cover_rows", "sdpcs_gen_cuts_csr", "sdpcs_triangle_rows_csr",
+    "sdpcs_set_cover_pattern", "sdpcs_get_cover_rows", "sdpcs_gen_cuts_csr", "sdpcs_triangle_rows_csr", "sdpcs_dense_eigcuts",
 ]
 
 NN_TCGEN05, NN_DMMA = 0, 1
@@ -243,6 +243,17 @@ class Engine(object):
         r = nrows.value
         nnz = int(rowptr[r])
         return dict(rowptr=rowptr[:r + 1], ind=ind[:nnz], val=val[:nnz], rhs=rhs[:r], src=src[:r])
+
+    def dense_eigcuts(self, vars_values):
+        """Strat 0 (cut_select_qp.py:757-786): dict(eigvals (n+1,), ind (width,), val (ncuts, width), rhs (ncuts,))."""
+        v = _f64(vars_values)
+        n = self.n
+        nb_lifted = n * (n + 1) // 2
+        width = n + nb_lifted
+        eig, val, rhs, nc = np.empty(n + 1), np.empty((n, width)), np.empty(n), c_i64()
+        self._ck(self._lib.sdpcs_dense_eigcuts(self._ctx, _ptr(v), c_i64(n), _ptr(eig), ctypes.byref(nc), _ptr(val), _ptr(rhs)))
+        ind = np.concatenate([np.arange(nb_lifted, nb_lifted + n), np.arange(nb_lifted)]).astype(np.int64)
+        return dict(eigvals=eig, ind=ind, val=val[:nc.value], rhs=rhs[:nc.value])
 
     def eigendecomp(self, d, curr_pt, X_slice, want_vecs=True):
         pt, Xs = _f64(curr_pt), _f64(X_slice)

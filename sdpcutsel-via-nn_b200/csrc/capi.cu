@@ -10,6 +10,7 @@
 #include "../../include/sdpcutsel.h"
 #include "aux_kernels.cuh"
 #include "cover_kernels.cuh"
+#include "dense_kernels.cuh"
 #include "score_kernels.cuh"
 #include "mlp_i8_kernels.cuh"
 #include "select_kernels.cuh"
@@ -1110,6 +1111,64 @@ extern "C" int sdpcs_triangle_rows_csr(int n, const int64_t* triple_rank, const 
         nnz += w;
         out_rowptr[r + 1] = nnz;
     }
+    return SDPCS_OK;
+}
+
+// Dense eigenvalue cuts, strat 0 (cut_select_qp.py:757-786): eigen-decomposition of the full [1 x^T; x X] on the
+// device (dense_kernels.cuh), one dense row per eigenvalue below thres_neg_eigval among the n smallest.
+extern "C" int sdpcs_dense_eigcuts(sdpcs_ctx* ctx, const double* vars_values, int64_t max_cuts, double* out_eigvals,
+                                   int64_t* out_ncuts, double* out_val, double* out_rhs)
+{
+    if (!ctx || !vars_values || !out_ncuts || max_cuts < 0) return SDPCS_ERR_INVALID;
+    *out_ncuts = 0;
+    if (!ctx->n) return ctx->fail(SDPCS_ERR_STATE, "set_instance first");
+    const int n = ctx->n, m = n + 1, mp = (m + 1) & ~1;
+    if (mp > DENSE_MAX_ORDER) return ctx->fail(SDPCS_ERR_INVALID, "dense eigcuts need n <= 255");
+    CU(cudaSetDevice(ctx->device));
+    int rc = upload_vars(ctx, vars_values);
+    if (rc) return rc;
+    const i64 width = (i64)n + (i64)n * (n + 1) / 2;
+    const size_t b_mat = sizeof(double) * mp * mp, b_eig = sizeof(double) * mp, b_cols = 1024 /* <= 256 ints */;
+    const i64 cap = std::min<i64>(max_cuts, n);
+    if ((rc = ensure_scratch(ctx, 2 * b_mat + b_eig + b_cols + 256 + sizeof(double) * (size_t)cap * (width + 1)))) return rc;
+    char* sc = static_cast<char*>(ctx->d_scratch);
+    DenseEigArgs a;
+    a.n = n; a.mp = mp;
+    a.X = ctx->d_vars; a.x = ctx->d_vars + (size_t)n * (n + 1) / 2;
+    a.A = reinterpret_cast<double*>(sc); a.V = reinterpret_cast<double*>(sc + b_mat); a.eig = reinterpret_cast<double*>(sc + 2 * b_mat);
+    int* d_cols = reinterpret_cast<int*>(sc + 2 * b_mat + b_eig);
+    a.sweeps_done = d_cols + 255;
+    a.max_sweeps = 30;
+    double* d_val = reinterpret_cast<double*>(sc + 2 * b_mat + b_eig + b_cols + 256);
+    double* d_rhs = d_val + (size_t)cap * width;
+    k_dense_jacobi<<<1, DENSE_THREADS, 0, ctx->stream>>>(a);
+    CU(cudaGetLastError());
+    std::vector<double> eig(mp);
+    int sweeps = 0;
+    CU(cudaMemcpyAsync(eig.data(), a.eig, b_eig, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&sweeps, a.sweeps_done, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (sweeps >= a.max_sweeps) return ctx->fail(SDPCS_ERR_CUDA, "dense Jacobi eigensolver did not converge");
+    // ascending order as LAPACK returns it; the padding row/column (mp > m) is an exact zero eigenvalue: drop one
+    std::vector<int> order;
+    for (int i = 0; i < m; ++i) order.push_back(i);
+    std::stable_sort(order.begin(), order.end(), [&](int p, int q) { return eig[p] < eig[q]; });
+    if (out_eigvals)
+        for (int i = 0; i < m; ++i) out_eigvals[i] = eig[order[i]];
+    std::vector<int> cols;
+    for (int ix = 0; ix < n; ++ix)                                 // the n smallest (cut_select_qp.py:772-773)
+        if (eig[order[ix]] < ctx->params.thres_neg_eigval) cols.push_back(order[ix]);
+    const i64 ncuts = (i64)cols.size();
+    *out_ncuts = ncuts;
+    if (ncuts == 0) return SDPCS_OK;
+    if (ncuts > max_cuts || !out_val || !out_rhs)
+        return ctx->fail(SDPCS_ERR_INVALID, "dense eigcuts: " + std::to_string(ncuts) + " cuts, output capacity " + std::to_string(max_cuts));
+    CU(cudaMemcpyAsync(d_cols, cols.data(), sizeof(int) * ncuts, cudaMemcpyHostToDevice, ctx->stream));
+    k_dense_rows<<<dim3((unsigned)(n + 1), (unsigned)ncuts), 256, 0, ctx->stream>>>(n, mp, a.V, d_cols, d_val, d_rhs);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out_val, d_val, sizeof(double) * (size_t)ncuts * width, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(out_rhs, d_rhs, sizeof(double) * ncuts, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return SDPCS_OK;
 }
 

@@ -7,6 +7,7 @@ Same method names, argument meaning, return formats and error behaviour as the r
     _gen_eigcuts_selected          (cut_select_qp.py:705-755)
     _get_eigendecomp               (cut_select_qp.py:788-797)
     __preprocess_triangle_ineq / __separate_and_add_triangle (cut_select_qp.py:799-863)
+    __gen_dense_eigcuts            (cut_select_qp.py:757-786, strat 0)
 but every score, selection and cut is computed by libsdpcutsel on the GPU.  The CPLEX LP loop
 (cut_select_algo), the instance readers and McCormick rows stay the reference's: mix this class in front of it
  -- ``class CutSolver(B200CutSelection, reference.CutSolver)`` -- or use it standalone through
@@ -86,7 +87,7 @@ class B200CutSelection(object):
         if dim is not None:
             self._dim = dim
         self._my_prob = my_prob if my_prob is not None else _Prob()
-        self._agg_list, self._tri_engine = [], None
+        self._agg_list, self._tri_engine, self._dense_engine = [], None, None
 
     # -- engines ---------------------------------------------------------------------------------------
     def _new_engine(self):
@@ -227,6 +228,19 @@ class B200CutSelection(object):
         vals, vecs = eng.eigendecomp(dim_subpr, curr_pt, X_slice, want_vecs=bool(ev_yes))
         return (vals, vecs) if ev_yes else vals
 
+    def _dense_eigcuts(self, vars_values=None):
+        """Strat 0 (cut_select_qp.py:757-786): one dense row per negative eigenvalue of the full [1 x^T; x X]."""
+        if getattr(self, "_dense_engine", None) is None:
+            self._dense_engine = self._new_engine()
+        d = self._dense_engine.dense_eigcuts(vars_values)
+        nb, width = d["val"].shape
+        csr = dict(rowptr=np.arange(nb + 1, dtype=np.int64) * width, ind=np.tile(d["ind"], nb), val=d["val"].ravel(), rhs=d["rhs"])
+        if not _add_rows_csr(self._my_prob, csr):
+            ind = d["ind"].tolist()
+            self._my_prob.linear_constraints.add(lin_expr=[SparsePair(ind=ind, val=row.tolist()) for row in d["val"]],
+                                                 rhs=d["rhs"].tolist(), senses=["G"] * nb)
+        return nb
+
     # name-mangled exactly like the reference's private triangle methods (_CutSolver__...)
     def _tri_preprocess(self):
         n = self._nb_vars
@@ -312,6 +326,9 @@ class CutSolver(B200CutSelection):
 
     def __init__(self):
         super(CutSolver, self).__init__()
+
+    def __gen_dense_eigcuts(self, vars_values=None):   # -> _CutSolver__gen_dense_eigcuts
+        return self._dense_eigcuts(vars_values)
 
     def __preprocess_triangle_ineq(self):          # -> _CutSolver__preprocess_triangle_ineq
         return self._tri_preprocess()
