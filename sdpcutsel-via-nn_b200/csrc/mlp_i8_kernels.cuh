@@ -42,7 +42,7 @@ constexpr int I8_TILE_BYTES = I8_A0_BYTES + I8_AUX_BYTES; // bytes per tile in t
 constexpr int I8_W0_BYTES = I8_NS * I8_N * I8_K0;         // 14336
 constexpr int I8_WH_BYTES = I8_NS * I8_N * 64;            // 28672
 constexpr int I8_EPI_WARPS = 16;
-constexpr int I8_THREADS = (I8_EPI_WARPS + 2) * 32;       // 576
+constexpr int I8_THREADS = (I8_EPI_WARPS + 4) * 32;       // 640: 16 epilogue warps + one warp group of helpers (MMA, TMA, 2 idle)
 constexpr int I8_NBAR = 2 * I8_SLOTS + 8;                 // slot_full[8] slot_empty[8] a0_full[2] lane_free[2] act_ready[2] y_ready[2]
 
 // instruction descriptor: D = S32, B = signed int8, A = unsigned int8 (bit 7 set: signed, for the top slice), both
@@ -184,6 +184,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint
 }
 __device__ __forceinline__ void umma_i8(uint32_t taddr, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
+#if defined(I8_EXP) && I8_EXP == 7
+    return;                                         // experiment: pipeline and epilogue without tensor-core work
+#endif
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(taddr),
                  "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
                  : "memory");
@@ -476,8 +479,17 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
     const i64 npair = (t1 - t0 + 1) / 2;
+    // register re-partitioning (per warp group): the helper warps keep 24 registers, the epilogue warps take 112 (20 x 96 = 4 x 24 + 16 x 114 per thread: an increase beyond the pool released by the helpers would block for ever) --
+    // with 227 KB of shared memory there is no L1 left for spills, every spilled value is an L2 round trip
+    // (the instruction sits at the head of each role's branch so that ptxas allocates each role within its own budget)
 
-    if (warp == I8_EPI_WARPS + 1) {
+#if defined(I8_EXP) && I8_EXP == 5
+    if (warp >= I8_EPI_WARPS) goto done;          // experiment: epilogue arithmetic alone, no pipeline
+#endif
+    if (warp > I8_EPI_WARPS + 1) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");      // idle members of the helper warp group
+    } else if (warp == I8_EPI_WARPS + 1) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
         // ===== TMA producer (whole warp walks the tile list, one elected lane issues the bulk copies) =====
         bool ok = true;
         for (i64 tile = t0; tile < t1 && ok; ++tile) {
@@ -496,6 +508,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
             __syncwarp();
         }
     } else if (warp == I8_EPI_WARPS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
         // ===== MMA issuer (whole warp walks the schedule and waits, one elected lane issues) =====
         // One accumulator stage: diagonal d lives in TMEM columns [64 d, 64 d + 64).  The stage is handed to the
         // epilogue with one commit per step and handed back once every epilogue warp has read it, so the MMAs of
@@ -551,6 +564,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                     ++step;
                 }
     } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
         // ===== epilogue warps =====
         const int q = warp & 3, cq = warp >> 2;
         const int row = q * 32 + lane;
@@ -564,11 +578,13 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                     const i64 tile = t0 + 2 * p + ln;
                     if (tile >= t1) continue;
                     I8_STAMP(step, 0);
+#if !(defined(I8_EXP) && I8_EXP == 5)
                     if (l == 0)   // acquire the TMA-written aux block of this tile (read in the last layer)
                         ok = mbar_wait(B_A0 + 8 * ln, (uint32_t)p & 1, abort_flag, a.status);
                     if (ok) ok = mbar_wait(B_FULL, step & 1, abort_flag, a.status);
                     ok = __all_sync(0xffffffffu, ok);
                     if (!ok) break;
+#endif
                     I8_STAMP(step, 1);
                     tc_fence_after();
 #ifdef SDPCS_I8_QSYNC
@@ -583,6 +599,16 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
                         uint32_t v0[8], v1[8], v2[8], v3[8], v4[8], v5[8], v6[8];
+#if defined(I8_EXP) && I8_EXP == 5
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            v0[j] = step + j; v1[j] = lane * 3 + j; v2[j] = step * lane; v3[j] = step ^ (j * 77);
+                            v4[j] = lane + 5 * j; v5[j] = step * 9 + lane; v6[j] = j * lane + step;
+                        }
+                        if (false) {
+#else
+                        {
+#endif
                         tmem_ld8_async(tbase + 0 * I8_N + half * 8, v0);
                         tmem_ld8_async(tbase + 1 * I8_N + half * 8, v1);
                         tmem_ld8_async(tbase + 2 * I8_N + half * 8, v2);
@@ -597,10 +623,15 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                             if (lane == 0) mbar_arrive(B_EMPTY);
                             I8_STAMP(step, 2);
                         }
+                        }
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             // value = accH * 2^32 + accL (exact integers, pre-biased so that the bit pattern is the
                             // double 1.5 * 2^52 + acc), one rounding; z = -2 log2(e) * (W a + b)
+#if defined(I8_EXP) && (I8_EXP == 3 || I8_EXP == 4)
+                            z[half * 8 + j] = __hiloint2double(0x3fe00000 | (v3[j] & 0xfffff), v6[j] ^ v0[j] ^ v1[j] ^ v2[j] ^ v4[j] ^ v5[j]);
+                            continue;
+#endif
                             long long accH = I8_MAGIC52_BITS, accL = I8_MAGIC52_BITS;
                             accH = (long long)(int)v0[j] * 65536ll + accH;
                             accH = (long long)(int)v1[j] * 256ll + accH;
@@ -630,8 +661,17 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                         double zz[4], act[4];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) zz[i] = z[g * 4 + i];
+#if defined(I8_EXP) && (I8_EXP == 1 || I8_EXP == 4)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) act[i] = zz[i] * 1e-3;
+#else
                         tansig_scaled_vec<4>(zz, act, tab);
+#endif
+#if defined(I8_EXP) && (I8_EXP == 2 || I8_EXP == 4)
+                        if (false) {
+#else
                         if (l < NHID - 1) {
+#endif
                             unsigned long long u[4];
 #pragma unroll
                             for (int i = 0; i < 4; ++i) u[i] = i8_quantize(act[i], 2251799813685248.0 /* 2^51 */);
@@ -656,6 +696,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                             for (int i = 0; i < 4; ++i) part = fma(wout[g * 4 + i], act[i], part);
                         }
                     }
+#if defined(I8_EXP) && I8_EXP == 5
+                    if (l == NHID - 1 && part == 123.456) a.obj[0] = part;
+                    if (true) {
+                    } else
+#endif
                     if (l < NHID - 1) {
                         fence_async_smem();
                         __syncwarp();
@@ -686,6 +731,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                     ++step;
                 }
     }
+#if defined(I8_EXP) && I8_EXP == 5
+done:
+#endif
     tc_fence_before();
     __syncthreads();
     if (warp == I8_EPI_WARPS)
