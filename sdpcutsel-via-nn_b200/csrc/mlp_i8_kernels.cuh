@@ -85,6 +85,9 @@ struct MlpI8Args {
 
 // Optional pipeline trace (tools/i8_trace.py builds a second library with -DSDPCS_I8_TRACE): CTA 0 stamps clock64 at
 // four points of steps 64 .. 64 + I8_TRACE_STEPS of every warp.  Compiled out of the product library.
+#ifndef I8_EXPF
+#define I8_EXPF 0
+#endif
 #ifdef SDPCS_I8_TRACE
 constexpr int I8_TRACE_STEPS = 96;
 __device__ long long g_i8_trace[I8_EPI_WARPS + 2][I8_TRACE_STEPS][4];
@@ -484,7 +487,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
     // (the instruction sits at the head of each role's branch so that ptxas allocates each role within its own budget)
 
 #if defined(I8_EXP) && I8_EXP == 5
-    if (warp >= I8_EPI_WARPS) goto done;          // experiment: epilogue arithmetic alone, no pipeline
+    if (warp >= I8_EPI_WARPS) {                   // experiment: epilogue arithmetic alone, no pipeline
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        goto done;
+    }
 #endif
     if (warp > I8_EPI_WARPS + 1) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");      // idle members of the helper warp group
@@ -599,7 +605,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
                         uint32_t v0[8], v1[8], v2[8], v3[8], v4[8], v5[8], v6[8];
-#if defined(I8_EXP) && I8_EXP == 5
+#if defined(I8_EXP) && I8_EXP == 5 && !(I8_EXPF & 1)
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             v0[j] = step + j; v1[j] = lane * 3 + j; v2[j] = step * lane; v3[j] = step ^ (j * 77);
@@ -617,12 +623,16 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                         tmem_ld8_async(tbase + 5 * I8_N + half * 8, v5);
                         tmem_ld8_async(tbase + 6 * I8_N + half * 8, v6);
                         tmem_wait_ld();
+#if defined(I8_EXP) && I8_EXP == 5
+                        if (half == 1 && (I8_EXPF & 4)) { tc_fence_before(); __syncwarp(); }
+#else
                         if (half == 1) {
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive(B_EMPTY);
                             I8_STAMP(step, 2);
                         }
+#endif
                         }
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
@@ -699,6 +709,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
 #if defined(I8_EXP) && I8_EXP == 5
                     if (l == NHID - 1 && part == 123.456) a.obj[0] = part;
                     if (true) {
+                        if (I8_EXPF & 2) { fence_async_smem(); __syncwarp(); }
                     } else
 #endif
                     if (l < NHID - 1) {
