@@ -137,6 +137,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nn-engine", default="tcgen05", choices=["tcgen05", "dmma"],
                     help="NN_rhoD evaluation: int8-sliced tcgen05 contraction (default) or FP64 DMMA")
+    ap.add_argument("--fused-prep", action="store_true",
+                    help="tcgen05 engine: build the layer-0 digit images in the MLP kernel's producer warps (no image in HBM)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -166,7 +168,7 @@ def main():
     with torch.cuda.stream(stream):
         eng = pkg._capi.Engine(local_rank)
         eng.set_stream(stream.cuda_stream)
-        eng.set_params(nn_engine=pkg._capi.NN_DMMA if args.nn_engine == "dmma" else pkg._capi.NN_TCGEN05)
+        eng.set_params(nn_engine=pkg._capi.NN_DMMA if args.nn_engine == "dmma" else pkg._capi.NN_TCGEN05, nn_fused_prep=int(args.fused_prep))
         eng.set_weights(rho, pkg.nn_weights.load_packed(rho))
         eng.set_instance(n, Q_arr)
         eng.set_cover_all(rho, r0, r1)
@@ -216,7 +218,7 @@ def main():
         if args.nn_engine == "tcgen05":
             eng.set_params(nn_engine=pkg._capi.NN_DMMA)
             res_dmma = sel.select(args.strat, None, k)
-            eng.set_params(nn_engine=pkg._capi.NN_TCGEN05)
+            eng.set_params(nn_engine=pkg._capi.NN_TCGEN05, nn_fused_prep=int(args.fused_prep))
             engines_agree = bool(np.array_equal(res["idx"], res_dmma["idx"]))
         t = torch.tensor([ms_dev, ms_e2e, score_ms / args.steps, nn_ms / args.steps, select_ms / args.steps], dtype=torch.float64, device=dev)
         if world > 1:

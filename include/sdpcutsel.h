@@ -47,7 +47,8 @@ typedef struct sdpcs_params {
     int32_t jacobi_sweeps;   /* scoring: 0 = Householder tridiagonalisation + Laguerre (default), > 0 = cyclic
                               * Jacobi with that many sweeps; cut generation always uses Jacobi (needs vectors) */
     int32_t nn_engine;       /* NN_rhoD evaluation: SDPCS_NN_TCGEN05 (default) or SDPCS_NN_DMMA */
-    int32_t reserved;        /* 0 */
+    int32_t nn_fused_prep;   /* tcgen05 engine: 0 = layer-0 digit images staged through HBM by a separate kernel (default),
+                              * 1 = built in shared memory by producer warps of the MLP kernel (no image in HBM) */
 } sdpcs_params;
 
 /* NN engines.  Both evaluate neural_net_{2..5}D (cut_select_qp.py:579-582) to FP64 accuracy:

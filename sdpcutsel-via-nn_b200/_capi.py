@@ -29,7 +29,7 @@ NN_TCGEN05, NN_DMMA = 0, 1
 class Params(ctypes.Structure):
     _fields_ = [("thres_min_opt", c_dbl), ("thres_neg_eigval", c_dbl), ("big_m", c_dbl), ("thres_tri_viol", c_dbl),
                 ("thres_tri_dense", ctypes.c_int32), ("jacobi_sweeps", ctypes.c_int32), ("nn_engine", ctypes.c_int32),
-                ("reserved", ctypes.c_int32)]
+                ("nn_fused_prep", ctypes.c_int32)]
 
 
 class Timings(ctypes.Structure):

@@ -237,7 +237,7 @@ extern "C" int sdpcs_default_params(sdpcs_params* p)
     p->thres_tri_dense = 2;
     p->jacobi_sweeps = 0;
     p->nn_engine = SDPCS_NN_TCGEN05;
-    p->reserved = 0;
+    p->nn_fused_prep = 0;
     return SDPCS_OK;
 }
 
@@ -623,11 +623,11 @@ static int ensure_tiles(sdpcs_ctx* ctx, i64 n_tiles)
     return SDPCS_OK;
 }
 
-template <int NHID>
+template <int NHID, int D>
 static int launch_mlp_i8(sdpcs_ctx* ctx, const MlpI8Args& m)
 {
     using L = I8Smem<NHID>;
-    auto kern = k_mlp_i8<NHID>;
+    auto kern = k_mlp_i8<NHID, D>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     const unsigned grid = (unsigned)std::max<i64>(1, std::min<i64>(m.n_tiles, ctx->sms));
     kern<<<grid, I8_THREADS, L::TOTAL, ctx->stream>>>(m);
@@ -635,9 +635,10 @@ static int launch_mlp_i8(sdpcs_ctx* ctx, const MlpI8Args& m)
     return SDPCS_OK;
 }
 
-// optimality measure of the N candidates described by `a` through the tcgen05 int8-sliced MLP
+// optimality measure of the N candidates described by `a` through the tcgen05 int8-sliced MLP, layer-0 digit images
+// staged through HBM in chunks by k_prep_i8 (default: faster today) --
 template <int D>
-static int launch_nn_i8(sdpcs_ctx* ctx, const ScoreArgs& a, i64 N)
+static int launch_nn_i8_staged(sdpcs_ctx* ctx, const ScoreArgs& a, i64 N)
 {
     if (!ctx->d_wi8[D]) return ctx->fail(SDPCS_ERR_STATE, "NN_" + std::to_string(D) + "D weights not set");
     const i64 total_tiles = (N + I8_M - 1) / I8_M;
@@ -657,9 +658,26 @@ static int launch_nn_i8(sdpcs_ctx* ctx, const ScoreArgs& a, i64 N)
         MlpI8Args m;
         m.wimg = ctx->d_wi8[D]; m.tiles = ctx->d_tiles; m.n_tiles = nt; m.n_rows = rows; m.out_base = c0;
         m.pos = a.pos; m.obj = a.obj; m.dbg_z = nullptr; m.dbg_layer = -1; m.status = ctx->d_status;
-        if ((rc = launch_mlp_i8<NetCfg<D>::NHID>(ctx, m))) return rc;
+        if ((rc = launch_mlp_i8<NetCfg<D>::NHID, 0>(ctx, m))) return rc;
         ctx->tm.score_launches += 2;
     }
+    ctx->i8_used = true;
+    return SDPCS_OK;
+}
+
+// optimality measure of the N candidates described by `a` through the tcgen05 int8-sliced MLP: ONE persistent launch,
+// unranking / gathering / slicing happen in the kernel's producer warp (nothing but the scores touches HBM)
+template <int D>
+static int launch_nn_i8(sdpcs_ctx* ctx, const ScoreArgs& a, i64 N)
+{
+    if (!ctx->d_wi8[D]) return ctx->fail(SDPCS_ERR_STATE, "NN_" + std::to_string(D) + "D weights not set");
+    if (!ctx->params.nn_fused_prep) return launch_nn_i8_staged<D>(ctx, a, N);
+    MlpI8Args m;
+    m.wimg = ctx->d_wi8[D]; m.s = a; m.tiles = nullptr; m.n_tiles = (N + I8_M - 1) / I8_M; m.n_rows = N; m.out_base = 0;
+    m.pos = a.pos; m.obj = a.obj; m.dbg_z = nullptr; m.dbg_layer = -1; m.status = ctx->d_status;
+    int rc = launch_mlp_i8<NetCfg<D>::NHID, D>(ctx, m);
+    if (rc) return rc;
+    ctx->tm.score_launches += 1;
     ctx->i8_used = true;
     return SDPCS_OK;
 }
@@ -1292,7 +1310,7 @@ static int launch_nn_i8_raw(sdpcs_ctx* ctx, const double* d_in, i64 m, double* d
         MlpI8Args a;
         a.wimg = ctx->d_wi8[D]; a.tiles = ctx->d_tiles; a.n_tiles = nt; a.n_rows = rows; a.out_base = c0;
         a.pos = nullptr; a.obj = d_out; a.dbg_z = d_z ? d_z + c0 * 64 : nullptr; a.dbg_layer = dbg_layer; a.status = ctx->d_status;
-        if ((rc = launch_mlp_i8<NetCfg<D>::NHID>(ctx, a))) return rc;
+        if ((rc = launch_mlp_i8<NetCfg<D>::NHID, 0>(ctx, a))) return rc;
     }
     return SDPCS_OK;
 }

@@ -66,13 +66,16 @@ struct I8Smem {
     static constexpr int P_CS = 0, P_BS = NHID * 64, P_WOUT = 2 * NHID * 64, P_MISC = P_WOUT + 64, P_TAB = P_MISC + 4;
     static constexpr int PAR = P_TAB + 256;
     static constexpr int OFF_BAR = OFF_PAR + PAR * 8;
-    static constexpr int TOTAL = OFF_BAR + I8_NBAR * 8 + 16;
+    static constexpr int OFF_XG = OFF_BAR + I8_NBAR * 8 + 16;               // mapminmax xoffset[24], gain[24] (fused producer)
+    static constexpr int TOTAL = OFF_XG + 2 * 24 * 8;
     static constexpr int GLOBAL_BYTES = W_TOTAL + PAR * 8;                 // device blob: images then parameters
 };
 
 struct MlpI8Args {
     const uint8_t* wimg;     // weight digit images followed by the FP64 parameter block (I8Smem::GLOBAL_BYTES)
-    const uint8_t* tiles;    // n_tiles x I8_TILE_BYTES written by k_prep_i8
+    ScoreArgs s;             // tiles == nullptr: instance, cover and LP point; the producer warp unranks, gathers and
+                             // slices the layer-0 digit image of each tile straight into shared memory (K1 + K2)
+    const uint8_t* tiles;    // raw-input mode (sdpcs_nn_eval): n_tiles x I8_TILE_BYTES written by k_prep_i8_raw, TMA loaded
     i64 n_tiles;
     i64 n_rows;              // valid candidates in this chunk
     i64 out_base;            // local candidate index of row 0 of the chunk
@@ -433,9 +436,91 @@ __global__ void __launch_bounds__(256) k_prep_i8_raw(const double* wfrag, const 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// K1 + K2 inside the MLP kernel: one row (candidate) of a layer-0 tile image, written straight into the lane's A
+// buffer in shared memory by the producer warp.  Same per-candidate arithmetic, operation for operation, as
+// k_score_nn / k_prep_i8 (cut_select_qp.py:536-538, 573-575; neural_net_3D.m:69-73), but streamed four inputs at a
+// time so that it fits the 64 registers of the helper warp group.
+// img: [slice s][k chunk (2)][128 rows][16 B]; aux: base[128], max_elem[128].
+// ---------------------------------------------------------------------------------------------------
+template <int D>
+__device__ __forceinline__ void i8_prep_row_smem(const ScoreArgs& a, const int (&c)[D], bool valid, int row, uint8_t* img, double* aux,
+                                                 const double* __restrict__ sxo, const double* __restrict__ sgn, int* status)
+{
+    using C = NetCfg<D>;
+    constexpr int T = D * (D + 1) / 2;
+    double Qs[T];
+    double mx = 0.0;
+    {
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = i; j < D; ++j) {
+                const double v = __ldg(a.Q + tri_index(a.n, c[i], c[j]));
+                Qs[k++] = v;
+                mx = fmax(mx, fabs(v));
+            }
+    }
+    double max_elem = (double)D * mx;
+    if (max_elem == 0.0) max_elem = 1.0;
+    const bool tiny = max_elem < 1e-280;
+    const double rme = fast_rcp(tiny ? 1.0 : max_elem);
+    double sdot = 0.0;
+    {
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = i; j < D; ++j) {
+                const double Xv = __ldg(a.X + tri_index(a.n, c[i], c[j]));
+                Qs[k] = tiny ? __ddiv_rn(Qs[k], max_elem) : div_by(Qs[k], max_elem, rme);
+                sdot = __dadd_rn(sdot, __dmul_rn(Qs[k], Xv));
+                ++k;
+            }
+    }
+    // zero the 32 bytes of every slice of this row, then overwrite four input digits at a time
+    uint8_t* rowp = img + row * 16;
+#pragma unroll
+    for (int sl = 0; sl < I8_NS; ++sl) {
+        *reinterpret_cast<uint4*>(rowp + sl * (I8_M * I8_K0)) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(rowp + sl * (I8_M * I8_K0) + I8_M * 16) = make_uint4(0, 0, 0, 0);
+    }
+    bool bad = false;
+#pragma unroll
+    for (int g = 0; g < (C::NIN + 3) / 4; ++g) {
+        unsigned long long u[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int k = 4 * g + t;
+            double pk = 0.0;
+            if (k < C::NIN) {
+                const double v = (k < D) ? __ldg(a.x + c[k < D ? k : 0]) : Qs[k >= D ? k - D : 0];
+                pk = __dadd_rn(__dmul_rn(__dsub_rn(v, sxo[k]), sgn[k]), -1.0);
+                if (!valid) pk = 0.0;
+                bad |= !(fabs(pk) < 2.0);
+            }
+            u[t] = i8_quantize(pk, 1125899906842624.0 /* 2^50 */);
+        }
+        uint8_t* dst = rowp + (g >> 2) * (I8_M * 16) + 4 * (g & 3);
+        *reinterpret_cast<uint32_t*>(dst + 6 * (I8_M * I8_K0)) = i8_pack4<0>(u[0], u[1], u[2], u[3]);
+        *reinterpret_cast<uint32_t*>(dst + 5 * (I8_M * I8_K0)) = i8_pack4<1>(u[0], u[1], u[2], u[3]);
+        *reinterpret_cast<uint32_t*>(dst + 4 * (I8_M * I8_K0)) = i8_pack4<2>(u[0], u[1], u[2], u[3]);
+        *reinterpret_cast<uint32_t*>(dst + 3 * (I8_M * I8_K0)) = i8_pack4<3>(u[0], u[1], u[2], u[3]);
+        *reinterpret_cast<uint32_t*>(dst + 2 * (I8_M * I8_K0)) = i8_pack4<4>(u[0], u[1], u[2], u[3]);
+        *reinterpret_cast<uint32_t*>(dst + 1 * (I8_M * I8_K0)) = i8_pack4<5>(u[0], u[1], u[2], u[3]);
+        *reinterpret_cast<uint32_t*>(dst + 0 * (I8_M * I8_K0)) = i8_pack4<6>(u[0], u[1], u[2], u[3]);
+    }
+    if (bad && valid) atomicCAS(status, 0, 2);
+    aux[row] = valid ? __dmul_rn(-sdot, max_elem) : 0.0;
+    aux[I8_M + row] = valid ? max_elem : 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // the MLP
 // ---------------------------------------------------------------------------------------------------
-template <int NHID>
+// D > 0: candidates come from the instance (the producer warp builds the layer-0 image in shared memory);
+// D = 0: raw network inputs, layer-0 images prepared by k_prep_i8_raw and loaded by TMA (sdpcs_nn_eval).
+template <int NHID, int D>
 __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
 {
     using L = I8Smem<NHID>;
@@ -457,6 +542,13 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
         for (int i = tid; i < L::W_TOTAL / 16; i += I8_THREADS) dst[i] = __ldg(src + i);
         const double* ps = reinterpret_cast<const double*>(a.wimg + L::W_TOTAL);
         for (int i = tid; i < L::PAR; i += I8_THREADS) par[i] = __ldg(ps + i);
+        if constexpr (D > 0) {
+            double* xg = reinterpret_cast<double*>(sm + L::OFF_XG);
+            if (tid < NetCfg<D>::NIN) {
+                xg[tid] = __ldg(a.s.wfrag + NetCfg<D>::OFF_XOFF + tid);
+                xg[24 + tid] = __ldg(a.s.wfrag + NetCfg<D>::OFF_GAIN + tid);
+            }
+        }
     }
     if (tid == 0) {
         for (int i = 0; i < I8_SLOTS; ++i) {
@@ -464,7 +556,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
             mbar_init(B_EMPTY + 8 * i, I8_EPI_WARPS);
         }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(B_A0 + 8 * i, 1);
+            mbar_init(B_A0 + 8 * i, D > 0 ? I8_M / 32 : 1);   // fused: one arrival per 32-row pass; TMA: expect_tx
             mbar_init(B_FREE + 8 * i, 1);
             mbar_init(B_ACT + 8 * i, I8_EPI_WARPS);
             mbar_init(B_Y + 8 * i, I8_EPI_WARPS);
@@ -482,39 +574,80 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
     const i64 npair = (t1 - t0 + 1) / 2;
-    // register re-partitioning (per warp group): the helper warps keep 24 registers, the epilogue warps take 112 (20 x 96 = 4 x 24 + 16 x 114 per thread: an increase beyond the pool released by the helpers would block for ever) --
+    // register re-partitioning (per warp group): the helper warps keep 24 (64 when they gather and slice the inputs themselves) registers, the epilogue warps take 112 (104): 20 x 96 >= 4 x 24 + 16 x 112 per thread -- an increase beyond the pool released by the helpers would block for ever;
     // with 227 KB of shared memory there is no L1 left for spills, every spilled value is an L2 round trip
     // (the instruction sits at the head of each role's branch so that ptxas allocates each role within its own budget)
 
 #if defined(I8_EXP) && I8_EXP == 5
     if (warp >= I8_EPI_WARPS) {                   // experiment: epilogue arithmetic alone, no pipeline
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         goto done;
     }
 #endif
-    if (warp > I8_EPI_WARPS + 1) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");      // idle members of the helper warp group
-    } else if (warp == I8_EPI_WARPS + 1) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-        // ===== TMA producer (whole warp walks the tile list, one elected lane issues the bulk copies) =====
+    if (warp > I8_EPI_WARPS + 1 && D == 0) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");      // idle members of the helper warp group (TMA mode)
+    } else if (warp >= I8_EPI_WARPS + 1) {
+        if constexpr (D > 0) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        // ===== producer: the layer-0 digit image of the next tile of each lane =====
         bool ok = true;
-        for (i64 tile = t0; tile < t1 && ok; ++tile) {
-            const int ln = (int)((tile - t0) & 1);
-            const uint32_t cnt = (uint32_t)((tile - t0) >> 1);
-            ok = mbar_wait_relaxed(B_FREE + 8 * ln, (cnt & 1) ^ 1, abort_flag, a.status);
-            ok = __all_sync(0xffffffffu, ok);
-            if (!ok) break;
-            if (elect_one()) {
-                mbar_expect_tx(B_A0 + 8 * ln, I8_TILE_BYTES);
-                const uint8_t* src = a.tiles + tile * (i64)I8_TILE_BYTES;
-                tma_load_1d(smem_u32(sm + L::OFF_A + ln * I8_AH_BYTES), src, I8_A0_BYTES, B_A0 + 8 * ln);
-                tma_load_1d(smem_u32(sm + L::OFF_AUX + (2 * ln + (cnt & 1)) * I8_AUX_BYTES), src + I8_A0_BYTES, I8_AUX_BYTES,
-                            B_A0 + 8 * ln);
+        if constexpr (D > 0) {
+            // K1 + K2 fused: unrank (once, then advance by 32 per pass), gather x / X / Q through L2, mapminmax, slice
+            const double* sxo = reinterpret_cast<const double*>(sm + L::OFF_XG);
+            const double* sgn = sxo + 24;
+            const bool all_mode = (a.s.idx == nullptr);
+            // three producer warps: 32-row pass g = 4 (tile - t0) + pass goes to warp g mod 3
+            constexpr int NPROD = 3;
+            const int pw = warp - (I8_EPI_WARPS + 1);
+            int c[D];
+#pragma unroll
+            for (int t = 0; t < D; ++t) c[t] = t;
+            bool live = all_mode && t0 * I8_M + pw * 32 + lane < a.n_rows;
+            if (live) lex_unrank<D>(a.s.n, (u64)(a.s.rank_begin + a.out_base + t0 * I8_M + pw * 32 + lane), c);
+            const i64 npass = (t1 - t0) * (I8_M / 32);
+            for (i64 g = pw; g < npass && ok; g += NPROD) {
+                const i64 tile = t0 + (g >> 2);
+                const int pass = (int)(g & 3);
+                const int ln = (int)((tile - t0) & 1);
+                const uint32_t cnt = (uint32_t)((tile - t0) >> 1);
+                ok = mbar_wait_relaxed(B_FREE + 8 * ln, (cnt & 1) ^ 1, abort_flag, a.status);
+                ok = __all_sync(0xffffffffu, ok);
+                if (!ok) break;
+                uint8_t* img = sm + L::OFF_A + ln * I8_AH_BYTES;
+                double* aux = reinterpret_cast<double*>(sm + L::OFF_AUX + (2 * ln + (cnt & 1)) * I8_AUX_BYTES);
+                const i64 r = tile * I8_M + pass * 32 + lane;
+                const bool valid = r < a.n_rows;
+                if (!all_mode) load_list_indices<D>(a.s.idx, a.out_base + r, valid, c);
+                i8_prep_row_smem<D>(a.s, c, valid, pass * 32 + lane, img, aux, sxo, sgn, a.status);
+                if (all_mode && !(valid && lex_advance<D>(a.s.n, c, 32 * NPROD))) {
+#pragma unroll
+                    for (int t = 0; t < D; ++t) c[t] = t;
+                }
+                fence_async_smem();          // generic-proxy writes -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(B_A0 + 8 * ln);
             }
-            __syncwarp();
+        } else {
+            // TMA (whole warp walks the tile list, one elected lane issues the bulk copies)
+            for (i64 tile = t0; tile < t1 && ok; ++tile) {
+                const int ln = (int)((tile - t0) & 1);
+                const uint32_t cnt = (uint32_t)((tile - t0) >> 1);
+                ok = mbar_wait_relaxed(B_FREE + 8 * ln, (cnt & 1) ^ 1, abort_flag, a.status);
+                ok = __all_sync(0xffffffffu, ok);
+                if (!ok) break;
+                if (elect_one()) {
+                    mbar_expect_tx(B_A0 + 8 * ln, I8_TILE_BYTES);
+                    const uint8_t* src = a.tiles + tile * (i64)I8_TILE_BYTES;
+                    tma_load_1d(smem_u32(sm + L::OFF_A + ln * I8_AH_BYTES), src, I8_A0_BYTES, B_A0 + 8 * ln);
+                    tma_load_1d(smem_u32(sm + L::OFF_AUX + (2 * ln + (cnt & 1)) * I8_AUX_BYTES), src + I8_A0_BYTES, I8_AUX_BYTES,
+                                B_A0 + 8 * ln);
+                }
+                __syncwarp();
+            }
         }
     } else if (warp == I8_EPI_WARPS) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        if constexpr (D > 0) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
         // ===== MMA issuer (whole warp walks the schedule and waits, one elected lane issues) =====
         // One accumulator stage: diagonal d lives in TMEM columns [64 d, 64 d + 64).  The stage is handed to the
         // epilogue with one commit per step and handed back once every epilogue warp has read it, so the MMAs of
@@ -570,7 +703,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                     ++step;
                 }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+        if constexpr (D > 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
         // ===== epilogue warps =====
         const int q = warp & 3, cq = warp >> 2;
         const int row = q * 32 + lane;

@@ -139,3 +139,44 @@ def test_sharded_rank_ranges_are_consistent(capi, blobs):
     eng.score(vv, 2)
     _, part = eng.scores(lam=False)
     assert np.array_equal(part, full[r0:r1])
+
+
+@pytest.mark.parametrize("rho", [2, 3, 4, 5])
+def test_fused_producer_is_bit_identical_to_the_staged_images(capi, blobs, golden, rho):
+    """nn_fused_prep = 1: the producer warps of k_mlp_i8 unrank / gather / slice in shared memory; same arithmetic as
+    k_prep_i8, so the scores are bit-identical -- all-subsets shards (ragged tile tails, mid-range start) and a
+    mixed-size pattern-E list cover."""
+    n = 31
+    Q_arr, adj = orc.boxqp_arrays(orc.synth_instance(n, 0.7, seed=40 + rho))
+    vv = orc.synth_point(n, seed=6)
+    out = []
+    for fused in (0, 1):
+        eng = capi.Engine(0)
+        eng.set_params(nn_fused_prep=fused)
+        for d in range(2, rho + 1):
+            eng.set_weights(d, blobs[d])
+        eng.set_instance(n, Q_arr)
+        res = []
+        N = capi.binom(n, rho)
+        for r0, r1 in ((0, N), (N // 3 + 5, 2 * N // 3 + 77), (7, 8)):
+            eng.set_cover_all(rho, r0, r1)
+            eng.score(vv, 2)
+            res.append(eng.scores(lam=False)[1])
+        assert eng.timings()["nn_fallbacks"] == 0
+        out.append(res)
+    for a, b in zip(*out):
+        assert np.array_equal(a, b)
+    if rho >= 3:
+        n2, Q2, adj2 = __import__("conftest").inst_arrays(golden, "spar040-030-1")
+        idx, sizes = orc.cover_pattern_E(adj2, rho)
+        got = []
+        for fused in (0, 1):
+            eng = capi.Engine(0)
+            eng.set_params(nn_fused_prep=fused)
+            for d in range(2, rho + 1):
+                eng.set_weights(d, blobs[d])
+            eng.set_instance(n2, Q2)
+            eng.set_cover_list(rho, idx)
+            eng.score(golden["mix_vars"], 2)
+            got.append(eng.scores(lam=False)[1])
+        assert np.array_equal(got[0], got[1])
