@@ -274,6 +274,8 @@ def main():
                            e2e_matches_resident=bool(np.array_equal(res["idx"], res_e2e["idx"])),
                            tcgen05_and_dmma_engines_select_identically=engines_agree),
         )
+        if sel.prof:
+            out["host_phase_ms_per_select"] = {k: 1e3 * v / (args.warmup + 2 * args.steps + (1 if args.nn_engine == "tcgen05" else 0)) for k, v in sel.prof.items()}
         if world == 1 and not args.no_cpu_baseline:
             sample_n = min(N, 1000000)
             dt = cpu_window_job((n, rho, wl["density"], 0, sample_n, k))

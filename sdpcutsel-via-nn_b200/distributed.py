@@ -4,6 +4,9 @@ local top-k; one small all-gather (k x 4 doubles per rank) plus an identical mer
 global selection. The combined strategy needs the global pivot, hence two gather rounds and one
 all-reduce of three counters.
 """
+import os
+import time
+
 import numpy as np
 
 
@@ -24,6 +27,12 @@ class ShardedSelector(object):
         except ImportError:
             self.dist = None
         self.world = self.dist.get_world_size(group) if self.dist else 1
+        self.prof = {} if os.environ.get("SDPCS_DIST_PROFILE") else None     # phase -> accumulated seconds (host clock)
+
+    def _t(self, name, t0):
+        if self.prof is not None:
+            self.prof[name] = self.prof.get(name, 0.0) + time.perf_counter() - t0
+        return time.perf_counter()
 
     # -- collectives on small host arrays ------------------------------------------------------------
     def _allgather(self, arr):
@@ -48,25 +57,31 @@ class ShardedSelector(object):
         self.dist.all_reduce(t, group=self.group)
         return t.cpu().numpy()
 
-    def _gather_merge(self, k, idx, score, lam, obj, use_obj2):
+    def _gather_merge(self, k, idx, score, lam, obj, use_obj2, counts=None):
+        """All-gather of the local lists (k + 1 rows of 4 doubles per rank) and the identical merge on every rank.
+        Row 0 carries the list length and, when given, the rank's three counters (they ride along instead of needing
+        their own all-reduce); returns (idx, score, lam, obj, summed counters or None)."""
         m = idx.shape[0]
         pack = np.zeros((k + 1, 4))
         pack[0, 0] = m
+        if counts is not None:
+            pack[0, 1:4] = counts          # < 2^44: exact in float64
         pack[1:m + 1, 0] = idx            # agg_idx < 2^44: exact in float64
         pack[1:m + 1, 1] = score
         pack[1:m + 1, 2] = lam
         pack[1:m + 1, 3] = obj
         allp = self._allgather(pack)
+        tot = allp[:, 0, 1:4].sum(axis=0).astype(np.int64) if counts is not None else None
         rows = np.concatenate([allp[r, 1:int(allp[r, 0, 0]) + 1] for r in range(self.world)], axis=0)
         if rows.shape[0] == 0:
             z = np.zeros(0)
-            return z.astype(np.int64), z, z, z
+            return z.astype(np.int64), z, z, z, tot
         gidx = rows[:, 0].astype(np.int64)
         if self.world == 1:
             perm = np.arange(min(k, rows.shape[0]))
         else:
             perm = self.eng.merge_topk(rows[:, 1], rows[:, 3] if use_obj2 else None, gidx, k)
-        return gidx[perm], rows[perm, 1], rows[perm, 2], rows[perm, 3]
+        return gidx[perm], rows[perm, 1], rows[perm, 2], rows[perm, 3], tot
 
     # -- public ------------------------------------------------------------------------------------
     def select(self, strat, vars_values, k, n_total=None):
@@ -76,21 +91,28 @@ class ShardedSelector(object):
         k = int(k)
         if strat not in (1, 2, 4):
             raise ValueError("strat must be 1, 2 or 4")
+        t = time.perf_counter()
         eng.score(vars_values, 1 if strat == 1 else 2 if strat == 2 else 3)
         if strat != 4:
             idx, sc, lam, obj = eng.topk(strat, k)
-            counts = self._allreduce_sum(eng.counts().astype(np.float64)).astype(np.int64)
-            gi, gs, gl, go = self._gather_merge(k, idx, sc, lam, obj, False)
+            t = self._t("score+topk", t)
+            gi, gs, gl, go, counts = self._gather_merge(k, idx, sc, lam, obj, False, eng.counts())
+            self._t("exchange+merge", t)
             return dict(idx=gi, score=gs, lam=gl, obj=go, counts=counts, new_strat=strat)
         idx, sc, lam, obj = eng.topk(3, k)
-        counts = self._allreduce_sum(eng.counts().astype(np.float64)).astype(np.int64)
+        t = self._t("score+topk1", t)
+        # the pivot of the combined rule needs k <= N; N is only known after the exchange, so gather k rows and cut after
+        si, ss, _, so, counts = self._gather_merge(k, idx, sc, lam, obj, False, eng.counts())
         N, n_viol, n_strong = (int(v) for v in counts)
         k = min(k, N)
-        si, ss, _, so = self._gather_merge(k, idx, sc, lam, obj, False)
+        si, so = si[:k], so[:k]
+        t = self._t("gather+merge1", t)
         all_walked = n_strong < k or k == 0
         pobj, pidx = (0.0, 0) if all_walked else (float(so[k - 1]), int(si[k - 1]))
         idx, sc, lam, obj = eng.topk(4, k, pobj, pidx, 1 if all_walked else 0)
-        gi, gs, gl, go = self._gather_merge(k, idx, sc, lam, obj, True)
+        t = self._t("topk2", t)
+        gi, gs, gl, go, _ = self._gather_merge(k, idx, sc, lam, obj, True)
+        self._t("gather+merge2", t)
         strong = min(n_strong, k)
         viol_walked = n_viol if all_walked else k
         new_strat = 4

@@ -1,0 +1,108 @@
+#!/usr/bin/env python
+"""Turn the raw outputs of tools/measure_round.sh (gpurun_out/<tag>_*) into the tracked summaries under profiles/.
+    python tools/summarise_round.py r01c v5        (tag of the measurement pass, version suffix of the files)"""
+import collections
+import csv
+import io
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag, ver = (sys.argv[1:] + ["r01c", "v5"])[:2]
+G = os.path.join(ROOT, "gpurun_out")
+P = os.path.join(ROOT, "profiles", "r01")
+os.makedirs(P, exist_ok=True)
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0, "nsecond": 1e-6}
+
+# ---- launch list ----------------------------------------------------------------------------------------
+src = os.path.join(G, tag + "_launches_cfg4.csv")
+rows = list(csv.reader(open(src)))
+hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+hdr = rows[hi]
+ix = {h: i for i, h in enumerate(hdr)}
+per = collections.OrderedDict()
+for r in rows[hi + 1:]:
+    if len(r) < len(hdr):
+        continue
+    d = per.setdefault(r[ix["ID"]], {"k": r[ix["Kernel Name"]].split("(")[0].replace("void ", "")})
+    d[r[ix["Metric Name"]]] = float(r[ix["Metric Value"]].replace(",", "")) * UNIT[r[ix["Metric Unit"]]]
+agg = collections.OrderedDict()
+for d in per.values():
+    a = agg.setdefault(d["k"], [0, 0.0, 0.0, 0.0])
+    a[0] += 1
+    a[1] += d["gpu__time_duration.sum"]
+    a[2] += d["dram__bytes_read.sum"]
+    a[3] += d["dram__bytes_write.sum"]
+shutil.copy(src, os.path.join(P, "ncu_launches_cfg4_%s.csv" % ver))
+tot = sum(a[1] for a in agg.values())
+lines = ["ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline",
+         "(first 400 launches: FP64 peak probes, 3 scoring passes of the tcgen05 engine, 1 of the DMMA engine, selection passes;",
+         " durations under ncu are cold-cache and serialised: read the SHARES)", "",
+         "%-28s %6s %12s %7s %12s %12s" % ("kernel", "count", "total ms", "share", "DRAM rd GB", "DRAM wr GB")]
+for k, a in agg.items():
+    lines.append("%-28s %6d %12.3f %6.1f%% %12.3f %12.3f" % (k[:28], a[0], a[1], 100 * a[1] / tot, a[2] / 1e9, a[3] / 1e9))
+nsteps = agg["k_mlp_i8<4, 0>" if "k_mlp_i8<4, 0>" in agg else [k for k in agg if k.startswith("k_mlp_i8")][0]][0] / 28.0
+mk = [k for k in agg if k.startswith("k_mlp_i8")][0]
+pk = [k for k in agg if k.startswith("k_prep_i8")][0]
+fk = [k for k in agg if k.startswith("k_score_feas")][0]
+per_step = {k: (agg[k][1] / (agg[k][0] / (28.0 if k != fk else 1.0)), (agg[k][2] + agg[k][3]) / (agg[k][0] / (28.0 if k != fk else 1.0))) for k in (mk, pk, fk)}
+lines += ["", "per scoring pass over 234,531,275 candidates (28 chunks): "
+          + "; ".join("%s %.1f ms, %.2f GB DRAM" % (k, v[0], v[1] / 1e9) for k, v in per_step.items())]
+open(os.path.join(P, "ncu_launches_cfg4_%s_summary.txt" % ver), "w").write("\n".join(lines) + "\n")
+print("\n".join(lines))
+
+# ---- full counters of the score kernels ------------------------------------------------------------------
+rep = os.path.join(G, tag + "_prof_cfg4.ncu-rep")
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rr = list(csv.reader(io.StringIO(raw)))
+h, units = rr[0], rr[1]
+keys = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread", "launch__occupancy_limit_registers",
+        "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+        "lts__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
+out = ["ncu --set full --clock-control none --import-source on -k 'regex:k_score_feas|k_prep_i8|k_mlp_i8' -c 3 python bench.py --steps 1 --warmup 1 --no-cpu-baseline",
+       "(cfg4; k_score_feas: whole shard of 234,531,275 candidates; k_prep_i8 / k_mlp_i8: first chunk of 65,536 tiles = 8,388,608 candidates)"]
+dram = {}
+for r in rr[2:]:
+    name = r[h.index("Kernel Name")]
+    out.append("== " + name)
+    for k in keys:
+        if k in h:
+            out.append("   %-72s %s %s" % (k, r[h.index(k)], units[h.index(k)]))
+    for i, hh in enumerate(h):
+        if "issue_stalled" in hh and "per_issue_active" in hh:
+            try:
+                v = float(r[i])
+            except ValueError:
+                continue
+            if v > 0.15:
+                out.append("   %-72s %s" % (hh.replace("smsp__average_warps_issue_stalled_", "stall ").replace("_per_issue_active.ratio", ""), r[i]))
+    dram[name] = (float(r[h.index("dram__bytes_read.sum")].replace(",", "")) * UNIT[units[h.index("dram__bytes_read.sum")]]
+                  + float(r[h.index("dram__bytes_write.sum")].replace(",", "")) * UNIT[units[h.index("dram__bytes_write.sum")]])
+open(os.path.join(P, "ncu_score_%s_cfg4_summary.txt" % ver), "w").write("\n".join(out) + "\n")
+print("\n".join(out[:8]))
+
+# ---- bench lines, traces -----------------------------------------------------------------------------------
+for a, b in (("_bench_n1.json", "bench_cfg4_%s_n1_default.json"), ("_bench_n1_dmma.json", "bench_cfg4_%s_n1_dmma_engine.json"),
+             ("_bench_ref.json", "bench_cfg4_%s_reference_arm.json"), ("_i8_trace.log", "i8_pipeline_trace_%s.txt"),
+             ("_cover_bench.log", "cover_build_%s.txt"), ("_tests.log", "gpu_tests_%s.log")):
+    f = os.path.join(G, tag + a)
+    if os.path.exists(f):
+        shutil.copy(f, os.path.join(P, b % ver))
+step_bytes = sum(v[1] for v in per_step.values())
+json.dump({"source": "profiles/r01/ncu_launches_cfg4_%s_summary.txt" % ver,
+           "kernels": {k: {"ms_per_pass": v[0], "dram_bytes_per_pass": v[1]} for k, v in per_step.items()},
+           "score_kernel_dram_bytes_per_launch": step_bytes,
+           "note": "one scoring pass over 234,531,275 candidates = 1 x k_score_feas + 28 x (k_prep_i8 + k_mlp_i8): dram__bytes_read.sum + "
+                   "dram__bytes_write.sum summed over those launches; algorithmic bytes = 16 B x candidates = 3.75e9 (lam + obj); the rest is the "
+                   "layer-0 digit image staged through HBM (240 B per candidate, written by k_prep_i8 and read back by TMA)"},
+          open(os.path.join(ROOT, "profiles", "ncu_summary.json"), "w"), indent=1)
+print("step DRAM bytes", step_bytes)
