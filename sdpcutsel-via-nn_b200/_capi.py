@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libsdpcutsel.so")
+LIB_PATH = os.environ.get("SDPCS_LIB") or os.path.join(_PKG, "libsdpcutsel.so")   # SDPCS_LIB: alternative build (trace / experiment libraries)
 
 c_i64, c_dbl, c_int, c_vp = ctypes.c_int64, ctypes.c_double, ctypes.c_int, ctypes.c_void_p
 P = ctypes.POINTER

@@ -1438,9 +1438,9 @@ extern "C" int sdpcs_fp64_peak(sdpcs_ctx* ctx, double* dfma_tflops, double* dmma
 // trace build only (tools/i8_trace.py): clock64 stamps of CTA 0, [warp 0..17][step][4]
 extern "C" int sdpcs_i8_trace_read(long long* out, int64_t cap)
 {
-    const size_t bytes = sizeof(long long) * (I8_EPI_WARPS + 2) * I8_TRACE_STEPS * 4;
+    const size_t bytes = sizeof(long long) * (I8_EPI_WARPS + 4) * I8_TRACE_STEPS * 4;
     if ((size_t)cap * sizeof(long long) < bytes) return SDPCS_ERR_INVALID;
     if (cudaMemcpyFromSymbol(out, g_i8_trace, bytes) != cudaSuccess) return SDPCS_ERR_CUDA;
-    return (I8_EPI_WARPS + 2) * I8_TRACE_STEPS * 4;
+    return (I8_EPI_WARPS + 4) * I8_TRACE_STEPS * 4;
 }
 #endif

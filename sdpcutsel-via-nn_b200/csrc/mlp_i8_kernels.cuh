@@ -93,7 +93,7 @@ struct MlpI8Args {
 #endif
 #ifdef SDPCS_I8_TRACE
 constexpr int I8_TRACE_STEPS = 96;
-__device__ long long g_i8_trace[I8_EPI_WARPS + 2][I8_TRACE_STEPS][4];
+__device__ long long g_i8_trace[I8_EPI_WARPS + 4][I8_TRACE_STEPS][4];
 #define I8_STAMP(STEP, K)                                                                                              \
     do {                                                                                                               \
         if (blockIdx.x == 0 && lane == 0 && (STEP) - 64u < (uint32_t)I8_TRACE_STEPS)                                   \
@@ -447,37 +447,27 @@ __device__ __forceinline__ void i8_prep_row_smem(const ScoreArgs& a, const int (
                                                  const double* __restrict__ sxo, const double* __restrict__ sgn, int* status)
 {
     using C = NetCfg<D>;
-    constexpr int T = D * (D + 1) / 2;
-    double Qs[T];
-    double mx = 0.0;
-    {
-        int k = 0;
-#pragma unroll
-        for (int i = 0; i < D; ++i)
-#pragma unroll
-            for (int j = i; j < D; ++j) {
-                const double v = __ldg(a.Q + tri_index(a.n, c[i], c[j]));
-                Qs[k++] = v;
-                mx = fmax(mx, fabs(v));
-            }
+#if defined(I8_EXP) && I8_EXP == 8
+    {   // experiment: producers that cost nothing (zero image)
+        uint8_t* rp = img + row * 16;
+        for (int sl = 0; sl < I8_NS; ++sl) {
+            *reinterpret_cast<uint4*>(rp + sl * (I8_M * I8_K0)) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(rp + sl * (I8_M * I8_K0) + I8_M * 16) = make_uint4(0, 0, 0, 0);
+        }
+        aux[row] = 0.0; aux[I8_M + row] = 1.0;
+        return;
     }
+#endif
+    // pass A: max |Q_slice| (the values are re-read in pass B: an L2 hit costs less than 30 live registers here)
+    double mx = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = i; j < D; ++j) mx = fmax(mx, fabs(__ldg(a.Q + tri_index(a.n, c[i], c[j]))));
     double max_elem = (double)D * mx;
     if (max_elem == 0.0) max_elem = 1.0;
     const bool tiny = max_elem < 1e-280;
     const double rme = fast_rcp(tiny ? 1.0 : max_elem);
-    double sdot = 0.0;
-    {
-        int k = 0;
-#pragma unroll
-        for (int i = 0; i < D; ++i)
-#pragma unroll
-            for (int j = i; j < D; ++j) {
-                const double Xv = __ldg(a.X + tri_index(a.n, c[i], c[j]));
-                Qs[k] = tiny ? __ddiv_rn(Qs[k], max_elem) : div_by(Qs[k], max_elem, rme);
-                sdot = __dadd_rn(sdot, __dmul_rn(Qs[k], Xv));
-                ++k;
-            }
-    }
     // zero the 32 bytes of every slice of this row, then overwrite four input digits at a time
     uint8_t* rowp = img + row * 16;
 #pragma unroll
@@ -486,29 +476,43 @@ __device__ __forceinline__ void i8_prep_row_smem(const ScoreArgs& a, const int (
         *reinterpret_cast<uint4*>(rowp + sl * (I8_M * I8_K0) + I8_M * 16) = make_uint4(0, 0, 0, 0);
     }
     bool bad = false;
-#pragma unroll
-    for (int g = 0; g < (C::NIN + 3) / 4; ++g) {
-        unsigned long long u[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const int k = 4 * g + t;
-            double pk = 0.0;
-            if (k < C::NIN) {
-                const double v = (k < D) ? __ldg(a.x + c[k < D ? k : 0]) : Qs[k >= D ? k - D : 0];
-                pk = __dadd_rn(__dmul_rn(__dsub_rn(v, sxo[k]), sgn[k]), -1.0);
-                if (!valid) pk = 0.0;
-                bad |= !(fabs(pk) < 2.0);
+    double sdot = 0.0;
+    unsigned long long u[4];
+    auto put = [&](int k, double v) {            // network input k (compile-time after unrolling): mapminmax, quantise, store
+        double pk = __dadd_rn(__dmul_rn(__dsub_rn(v, sxo[k]), sgn[k]), -1.0);
+        if (!valid) pk = 0.0;
+        bad |= !(fabs(pk) < 2.0);
+        u[k & 3] = i8_quantize(pk, 1125899906842624.0 /* 2^50 */);
+        if ((k & 3) == 3 || k == C::NIN - 1) {
+            if ((k & 3) != 3) {
+                for (int t = (k & 3) + 1; t < 4; ++t) u[t] = 0;
             }
-            u[t] = i8_quantize(pk, 1125899906842624.0 /* 2^50 */);
+            const int g = k >> 2;
+            uint8_t* dst = rowp + (g >> 2) * (I8_M * 16) + 4 * (g & 3);
+            *reinterpret_cast<uint32_t*>(dst + 6 * (I8_M * I8_K0)) = i8_pack4<0>(u[0], u[1], u[2], u[3]);
+            *reinterpret_cast<uint32_t*>(dst + 5 * (I8_M * I8_K0)) = i8_pack4<1>(u[0], u[1], u[2], u[3]);
+            *reinterpret_cast<uint32_t*>(dst + 4 * (I8_M * I8_K0)) = i8_pack4<2>(u[0], u[1], u[2], u[3]);
+            *reinterpret_cast<uint32_t*>(dst + 3 * (I8_M * I8_K0)) = i8_pack4<3>(u[0], u[1], u[2], u[3]);
+            *reinterpret_cast<uint32_t*>(dst + 2 * (I8_M * I8_K0)) = i8_pack4<4>(u[0], u[1], u[2], u[3]);
+            *reinterpret_cast<uint32_t*>(dst + 1 * (I8_M * I8_K0)) = i8_pack4<5>(u[0], u[1], u[2], u[3]);
+            *reinterpret_cast<uint32_t*>(dst + 0 * (I8_M * I8_K0)) = i8_pack4<6>(u[0], u[1], u[2], u[3]);
         }
-        uint8_t* dst = rowp + (g >> 2) * (I8_M * 16) + 4 * (g & 3);
-        *reinterpret_cast<uint32_t*>(dst + 6 * (I8_M * I8_K0)) = i8_pack4<0>(u[0], u[1], u[2], u[3]);
-        *reinterpret_cast<uint32_t*>(dst + 5 * (I8_M * I8_K0)) = i8_pack4<1>(u[0], u[1], u[2], u[3]);
-        *reinterpret_cast<uint32_t*>(dst + 4 * (I8_M * I8_K0)) = i8_pack4<2>(u[0], u[1], u[2], u[3]);
-        *reinterpret_cast<uint32_t*>(dst + 3 * (I8_M * I8_K0)) = i8_pack4<3>(u[0], u[1], u[2], u[3]);
-        *reinterpret_cast<uint32_t*>(dst + 2 * (I8_M * I8_K0)) = i8_pack4<4>(u[0], u[1], u[2], u[3]);
-        *reinterpret_cast<uint32_t*>(dst + 1 * (I8_M * I8_K0)) = i8_pack4<5>(u[0], u[1], u[2], u[3]);
-        *reinterpret_cast<uint32_t*>(dst + 0 * (I8_M * I8_K0)) = i8_pack4<6>(u[0], u[1], u[2], u[3]);
+    };
+#pragma unroll
+    for (int k = 0; k < D; ++k) put(k, __ldg(a.x + c[k]));
+    {
+        int k = D;
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = i; j < D; ++j) {
+                const int t = tri_index(a.n, c[i], c[j]);
+                const double Qv = __ldg(a.Q + t), Xv = __ldg(a.X + t);
+                const double Qt = tiny ? __ddiv_rn(Qv, max_elem) : div_by(Qv, max_elem, rme);
+                sdot = __dadd_rn(sdot, __dmul_rn(Qt, Xv));          // left-to-right, no FMA (cut_select_qp.py:575)
+                put(k, Qt);
+                ++k;
+            }
     }
     if (bad && valid) atomicCAS(status, 0, 2);
     aux[row] = valid ? __dmul_rn(-sdot, max_elem) : 0.0;
@@ -610,9 +614,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                 const int pass = (int)(g & 3);
                 const int ln = (int)((tile - t0) & 1);
                 const uint32_t cnt = (uint32_t)((tile - t0) >> 1);
+                I8_STAMP((uint32_t)(g / NPROD), 0);
                 ok = mbar_wait_relaxed(B_FREE + 8 * ln, (cnt & 1) ^ 1, abort_flag, a.status);
                 ok = __all_sync(0xffffffffu, ok);
                 if (!ok) break;
+                I8_STAMP((uint32_t)(g / NPROD), 1);
                 uint8_t* img = sm + L::OFF_A + ln * I8_AH_BYTES;
                 double* aux = reinterpret_cast<double*>(sm + L::OFF_AUX + (2 * ln + (cnt & 1)) * I8_AUX_BYTES);
                 const i64 r = tile * I8_M + pass * 32 + lane;
@@ -623,9 +629,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
 #pragma unroll
                     for (int t = 0; t < D; ++t) c[t] = t;
                 }
+                I8_STAMP((uint32_t)(g / NPROD), 2);
                 fence_async_smem();          // generic-proxy writes -> visible to the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(B_A0 + 8 * ln);
+                I8_STAMP((uint32_t)(g / NPROD), 3);
             }
         } else {
             // TMA (whole warp walks the tile list, one elected lane issues the bulk copies)
