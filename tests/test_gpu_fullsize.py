@@ -1,0 +1,106 @@
+"""GPU parity at BASELINE.json's full sizes (configs[2]: n = 125, rho = 4, 9,691,375 subsets; configs[3]: n = 125,
+rho = 5, 234,531,275 subsets), where the oracle cannot score everything in seconds:
+
+* rank windows (start, middle, ragged end of the enumeration) are scored by the oracle and compared value by value;
+* size-independent properties on the whole cover: the selection is idempotent, unique, sorted by the reference's key,
+  equal to the merge of per-shard selections (the multi-GPU decomposition), equal between the two NN engines, and the
+  5000 selected subsets re-scored by the oracle come out with the same scores (tolerance) and in the same order."""
+import numpy as np
+import pytest
+
+from oracle import cutsel_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+LAM_TOL = 1e-12
+OBJ_TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def capi():
+    import sdpcutsel_via_nn_b200 as pkg
+    return pkg._capi
+
+
+@pytest.fixture(scope="module")
+def inst():
+    n = 125
+    Q_arr, adj = orc.boxqp_arrays(orc.synth_instance(n, 0.75, seed=7))
+    return n, Q_arr, orc.synth_point(n, seed=8)
+
+
+def _engine(capi, blobs, n, Q_arr, rho, **params):
+    eng = capi.Engine(0)
+    if params:
+        eng.set_params(**params)
+    eng.set_weights(rho, blobs[rho])
+    eng.set_instance(n, Q_arr)
+    return eng
+
+
+@pytest.mark.parametrize("rho", [4, 5])
+def test_rank_windows_vs_oracle(capi, blobs, inst, rho):
+    n, Q_arr, vv = inst
+    N = capi.binom(n, rho)
+    eng = _engine(capi, blobs, n, Q_arr, rho)
+    w = 40000
+    for r0 in (0, N // 2 + 12345, N - w - 1, N - 77):
+        r1 = min(N, r0 + w)
+        idx = orc.cover_all_window(n, rho, r0, r1)
+        assert np.array_equal(idx, capi.unrank(n, rho, np.arange(r0, r1)))
+        lam_o, obj_o = orc.score_cover(Q_arr, n, idx, np.full(r1 - r0, rho), vv, blobs)
+        eng.set_cover_all(rho, r0, r1)
+        eng.score(vv, 3)
+        lam, obj = eng.scores()
+        assert np.abs(lam - lam_o).max() < LAM_TOL and np.abs(obj - obj_o).max() < OBJ_TOL
+        k = min(500, r1 - r0)
+        ns, order, score = orc.select_comb(obj_o, lam_o, k)
+        r = eng.select(4, vv, k)
+        assert r["new_strat"] == ns and np.array_equal(r["idx"] - r0, order[:k])
+
+
+@pytest.mark.parametrize("rho", [4, 5])
+def test_whole_cover_selection_properties(capi, blobs, inst, rho):
+    n, Q_arr, vv = inst
+    N = capi.binom(n, rho)
+    k = 5000
+    eng = _engine(capi, blobs, n, Q_arr, rho)
+    eng.set_cover_all(rho)
+    assert eng.num_candidates == N
+    r4 = eng.select(4, vv, k)
+    again = eng.select(4, None, k)                                     # LP point resident on the device
+    assert np.array_equal(r4["idx"], again["idx"]) and np.array_equal(r4["score"], again["score"])
+    assert np.unique(r4["idx"]).size == k and r4["idx"].min() >= 0 and r4["idx"].max() < N
+    assert int(r4["counts"][0]) == N
+    # optimality ranking: sorted by (score desc, index asc)
+    r2 = eng.select(2, None, k)
+    s, i = r2["score"], r2["idx"]
+    assert np.all((s[:-1] > s[1:]) | ((s[:-1] == s[1:]) & (i[:-1] < i[1:])))
+    # feasibility ranking: only violated subsets, sorted
+    r1 = eng.select(1, None, k)
+    assert np.all(r1["lam"] < -1e-15) and np.all(np.diff(r1["score"]) <= 0)
+    # merge of per-shard selections (what the sharded multi-GPU path does) == single-shot selection
+    cuts = [0, N // 3 + 5, 2 * N // 3 + 1, N]
+    parts = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        eng.set_cover_all(rho, a, b)
+        eng.score(vv, 2)
+        parts.append(eng.topk(2, k))
+    gidx = np.concatenate([p[0] for p in parts])
+    gsc = np.concatenate([p[1] for p in parts])
+    perm = eng.merge_topk(gsc, None, gidx, k)
+    assert np.array_equal(gidx[perm], r2["idx"]) and np.array_equal(gsc[perm], r2["score"])
+    # the FP64 DMMA engine selects the identical list
+    dm = _engine(capi, blobs, n, Q_arr, rho, nn_engine=capi.NN_DMMA)
+    dm.set_cover_all(rho)
+    rd = dm.select(4, vv, k)
+    assert np.array_equal(rd["idx"], r4["idx"]) and rd["new_strat"] == r4["new_strat"]
+    assert np.abs(rd["score"] - r4["score"]).max() < OBJ_TOL
+    # the selected subsets, re-scored by the oracle
+    sets = capi.unrank(n, rho, r2["idx"])
+    lam_o, obj_o = orc.score_cover(Q_arr, n, sets, np.full(k, rho), vv, blobs)
+    assert np.abs(obj_o - r2["score"]).max() < OBJ_TOL
+    assert np.array_equal(np.argsort(-obj_o, kind="stable"), np.arange(k))          # same order in the oracle's arithmetic
+    sets = capi.unrank(n, rho, r1["idx"])
+    lam_o, _ = orc.score_cover(Q_arr, n, sets, np.full(k, rho), vv, blobs, want_obj=False)
+    assert np.abs(-lam_o - r1["score"]).max() < LAM_TOL

@@ -42,7 +42,7 @@ def main():
     nin = rho * (rho + 3) // 2
     x = np.concatenate([rng.uniform(0, 1, (m, rho)), rng.uniform(-1.0 / rho, 1.0 / rho, (m, nin - rho))], axis=1)
     eng.nn_eval(rho, x)
-    nw, ns = 18, 96
+    nw, ns = 20, 96
     buf = np.zeros(nw * ns * 4, dtype=np.int64)
     rc = lib.sdpcs_i8_trace_read(buf.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(buf.size))
     assert rc == buf.size, rc
