@@ -983,10 +983,37 @@ extern "C" int sdpcs_merge_topk(sdpcs_ctx* ctx, int64_t m, const double* score, 
                                 int64_t k, int64_t* out_perm, int64_t* out_n)
 {
     if (!ctx || m < 0 || (m && (!score || !idx)) || !out_perm || !out_n) return SDPCS_ERR_INVALID;
-    CU(cudaSetDevice(ctx->device));
     *out_n = 0;
     if (m == 0 || k <= 0) return SDPCS_OK;
-    // scratch: score, obj2, idx, k1, k2, sorted k1/k2/idx, perm  (9 arrays of m)
+    const i64 take = std::min<i64>(k, m);
+    // order: key1 desc, key2 desc, agg_idx asc (= the device selection order, select_kernels.cuh)
+    auto before = [&](i64 a, i64 b) {
+        const u64 a1 = enc_key(score[a]), b1 = enc_key(score[b]);
+        if (a1 != b1) return a1 > b1;
+        const u64 a2 = obj2 ? enc_key(obj2[a]) : 0, b2 = obj2 ? enc_key(obj2[b]) : 0;
+        if (a2 != b2) return a2 > b2;
+        return idx[a] < idx[b];
+    };
+    // The callers hand over the concatenation of per-shard lists, each already in selection order: find the sorted
+    // runs and take the first k of their merge (k x runs comparisons on the host, no device round trip).
+    std::vector<i64> run_begin{0};
+    for (i64 i = 1; i < m; ++i)
+        if (before(i, i - 1)) run_begin.push_back(i);
+    const i64 runs = (i64)run_begin.size();
+    if (runs <= 256) {
+        std::vector<i64> head(run_begin), end(runs);
+        for (i64 r = 0; r < runs; ++r) end[r] = (r + 1 < runs) ? run_begin[r + 1] : m;
+        for (i64 o = 0; o < take; ++o) {
+            i64 best = -1;
+            for (i64 r = 0; r < runs; ++r)
+                if (head[r] < end[r] && (best < 0 || before(head[r], head[best]))) best = r;
+            out_perm[o] = head[best]++;
+        }
+        *out_n = take;
+        return SDPCS_OK;
+    }
+    // unsorted input: rank-counting sort of all m entries on the device
+    CU(cudaSetDevice(ctx->device));
     int rc = ensure_scratch(ctx, (size_t)m * 8 * 9);
     if (rc) return rc;
     double* d_score = (double*)ctx->d_scratch;
@@ -997,24 +1024,19 @@ extern "C" int sdpcs_merge_topk(sdpcs_ctx* ctx, int64_t m, const double* score, 
     u64* d_s1 = d_k2 + m;
     u64* d_s2 = d_s1 + m;
     i64* d_si = (i64*)(d_s2 + m);
-    i64* d_pp = d_si + m;
     CU(cudaMemcpyAsync(d_score, score, m * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (obj2) CU(cudaMemcpyAsync(d_obj2, obj2, m * 8, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(d_idx, idx, m * 8, cudaMemcpyHostToDevice, ctx->stream));
     k_merge_keys<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(m, d_score, obj2 ? d_obj2 : nullptr, d_k1, d_k2);
-    // rank sort all m entries (m = shards * k is small); positions travel in the "idx" payload of a second sort key
-    // -> sort by (k1, k2, idx) and recover the permutation by sorting the position array alongside
     k_rank_sort<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(nullptr, m, d_k1, d_k2, d_idx, d_s1, d_s2, d_si);
     CU(cudaGetLastError());
     std::vector<i64> sorted_idx(m), in_idx(idx, idx + m);
     CU(cudaMemcpyAsync(sorted_idx.data(), d_si, m * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    (void)d_pp;
     // agg_idx values are unique across shards: map them back to input positions
     std::vector<std::pair<i64, i64>> where(m);
     for (i64 i = 0; i < m; ++i) where[i] = {in_idx[i], i};
     std::sort(where.begin(), where.end());
-    const i64 take = std::min<i64>(k, m);
     for (i64 i = 0; i < take; ++i) {
         auto it = std::lower_bound(where.begin(), where.end(), std::make_pair(sorted_idx[i], (i64)-1));
         out_perm[i] = it->second;

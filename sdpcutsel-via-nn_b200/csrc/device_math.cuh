@@ -89,6 +89,7 @@ __host__ __device__ __forceinline__ int tri_index(int n, int i, int j) { return 
 // ---------------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ u64 enc_key(double x)
 {
+    x = x + 0.0;     // -0.0 -> +0.0: Python's sort (the reference) compares them equal, the tie then goes to the index
     u64 b;
 #ifdef __CUDA_ARCH__
     b = (u64)__double_as_longlong(x);

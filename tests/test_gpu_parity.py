@@ -277,3 +277,27 @@ def test_eigen_methods_vs_lapack(capi, blobs, golden, rho):
             eng.score(vv, 1)
             lam, _ = eng.scores(obj=False)
             assert np.abs(lam - lam_o).max() < 2e-14, (rho, sweeps)
+
+
+def test_merge_topk_sorted_runs_and_unsorted_input(capi):
+    """sdpcs_merge_topk: concatenated per-shard lists (sorted runs: host k-way merge) and arbitrary input (device rank
+    sort) both give the first k of the order (score desc, obj2 desc, agg_idx asc), ties included."""
+    rng = np.random.default_rng(12)
+    eng = capi.Engine(0)
+    for runs, per, with_obj2 in ((8, 5000, True), (2, 7, False), (1, 100, True), (300, 40, True)):
+        score = np.round(rng.normal(size=runs * per), 1)                 # many exact ties
+        obj2 = np.round(rng.normal(size=runs * per), 1)
+        idx = rng.permutation(runs * per).astype(np.int64)
+        rows = []
+        for r in range(runs):                                             # sort each run the way a shard would
+            sl = slice(r * per, (r + 1) * per)
+            o = np.lexsort((idx[sl], -obj2[sl] if with_obj2 else np.zeros(per), -score[sl]))
+            rows.append((score[sl][o], obj2[sl][o], idx[sl][o]))
+        score, obj2, idx = (np.concatenate([x[i] for x in rows]) for i in range(3))
+        for k in (1, per, runs * per, runs * per + 5):
+            want = np.lexsort((idx, -obj2 if with_obj2 else np.zeros(idx.size), -score))[:k]
+            got = eng.merge_topk(score, obj2 if with_obj2 else None, idx, k)
+            assert np.array_equal(got, want)
+    # unsorted input
+    score, idx = rng.normal(size=3000), rng.permutation(3000).astype(np.int64)
+    assert np.array_equal(eng.merge_topk(score, None, idx, 100), np.argsort(-score, kind="stable")[:100])
