@@ -45,12 +45,11 @@ struct KeyArgs {
 __global__ void __launch_bounds__(256) k_make_keys(KeyArgs a)
 {
     i64 nv = 0, ns = 0;
-    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < a.N; i += (i64)gridDim.x * blockDim.x) {
-        double lam = a.lam ? a.lam[i] : 0.0, obj = a.obj ? a.obj[i] : 0.0;
+    auto make = [&](i64 i, double lam, double obj, u64& k1, u64& k2) {
         bool viol = a.lam && lam < a.thr_eig;
         bool pos = a.obj && obj > a.thr_opt;
         nv += viol; ns += (viol && pos);
-        u64 k1 = 0, k2 = 0;
+        k1 = 0; k2 = 0;
         switch (a.mode) {
         case 1: k1 = viol ? enc_key(-lam) : 0; break;
         case 2: k1 = enc_key(obj); break;
@@ -66,6 +65,33 @@ __global__ void __launch_bounds__(256) k_make_keys(KeyArgs a)
             k1 = enc_key(f); k2 = enc_key(obj);
         } break;
         }
+    };
+    // 16-byte loads / stores, two pairs in flight per thread (HBM-bound pass: 16 B read + 8..16 B written per candidate)
+    const i64 tid = (i64)blockIdx.x * blockDim.x + threadIdx.x, nthr = (i64)gridDim.x * blockDim.x;
+    const i64 N4 = a.N & ~(i64)3;
+    for (i64 i = tid * 2; i < N4; i += nthr * 4) {
+        double2 L[2], O[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const i64 j = i + u * nthr * 2;
+            const bool in = j < N4;
+            L[u] = (in && a.lam) ? *reinterpret_cast<const double2*>(a.lam + j) : make_double2(0.0, 0.0);
+            O[u] = (in && a.obj) ? *reinterpret_cast<const double2*>(a.obj + j) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const i64 j = i + u * nthr * 2;
+            if (j >= N4) continue;
+            ulonglong2 K1, K2;
+            make(j, L[u].x, O[u].x, K1.x, K2.x);
+            make(j + 1, L[u].y, O[u].y, K1.y, K2.y);
+            *reinterpret_cast<ulonglong2*>(a.key1 + j) = K1;
+            if (a.key2) *reinterpret_cast<ulonglong2*>(a.key2 + j) = K2;
+        }
+    }
+    for (i64 i = N4 + tid; i < a.N; i += nthr) {
+        u64 k1, k2;
+        make(i, a.lam ? a.lam[i] : 0.0, a.obj ? a.obj[i] : 0.0, k1, k2);
         a.key1[i] = k1;
         if (a.key2) a.key2[i] = k2;
     }
@@ -115,15 +141,40 @@ __global__ void __launch_bounds__(512) k_sel_hist(SelArgs a, int level, int shif
     const int hs = shift + width;
     const unsigned mask = (1u << width) - 1;
     i64 nvalid = 0;
-    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < a.N; i += (i64)gridDim.x * blockDim.x) {
-        u64 k1 = a.key1[i];
+    // run-length aggregation per thread: the leading digits (sign + exponent of an FP64 score) put almost every key
+    // into the same two or three bins, and one shared-memory atomic per key would serialise on them
+    unsigned run_bin = 0, run_cnt = 0;
+    auto take = [&](i64 i, u64 k1) {
         if (count_valid) nvalid += (k1 != 0);
-        if (level >= 1 && k1 != T0) continue;
-        if (level == 2 && a.key2 && a.key2[i] != T1) continue;
+        if (level >= 1 && k1 != T0) return;
+        if (level == 2 && a.key2 && a.key2[i] != T1) return;
         u64 key = (level == 0) ? k1 : level_key(a, i, level);
-        if (hs < 64 && (key >> hs) != (prefix >> hs)) continue;
-        atomicAdd(&sh[(unsigned)(key >> shift) & mask], 1u);
+        if (hs < 64 && (key >> hs) != (prefix >> hs)) return;
+        const unsigned bin = (unsigned)(key >> shift) & mask;
+        if (bin == run_bin) ++run_cnt;
+        else {
+            if (run_cnt) atomicAdd(&sh[run_bin], run_cnt);
+            run_bin = bin; run_cnt = 1;
+        }
+    };
+    // four 16-byte loads in flight per thread: one 8-byte load per thread and iteration leaves HBM latency-bound
+    const i64 tid = (i64)blockIdx.x * blockDim.x + threadIdx.x, nthr = (i64)gridDim.x * blockDim.x;
+    const i64 N8 = a.N & ~(i64)7;
+    for (i64 i = tid * 2; i < N8; i += nthr * 8) {
+        ulonglong2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const i64 j = i + u * nthr * 2;
+            v[u] = (j < N8) ? *reinterpret_cast<const ulonglong2*>(a.key1 + j) : make_ulonglong2(0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const i64 j = i + u * nthr * 2;
+            if (j < N8) { take(j, v[u].x); take(j + 1, v[u].y); }
+        }
     }
+    for (i64 i = N8 + tid; i < a.N; i += nthr) take(i, a.key1[i]);
+    if (run_cnt) atomicAdd(&sh[run_bin], run_cnt);
     __syncthreads();
     for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x)
         if (sh[i]) atomicAdd(&st->hist[i], sh[i]);
@@ -195,18 +246,33 @@ __global__ void __launch_bounds__(256) k_sel_collect(SelArgs a, i64 cap, u64* ou
     SelState* st = a.st;
     if (st->k_eff <= 0) return;
     const u64 T0 = st->T[0], T1 = st->T[1], T2 = st->T[2];
-    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < a.N; i += (i64)gridDim.x * blockDim.x) {
-        u64 k1 = a.key1[i];
-        if (k1 < T0 || k1 == 0) continue;
+    auto take = [&](i64 i, u64 k1) {
+        if (k1 < T0 || k1 == 0) return;
         u64 k2 = a.key2 ? a.key2[i] : 0;
         i64 idx = a.idx ? a.idx[i] : a.base + i;
         if (k1 == T0) {
-            if (k2 < T1) continue;
-            if (k2 == T1 && (IDX_TOP - (u64)idx) < T2) continue;
+            if (k2 < T1) return;
+            if (k2 == T1 && (IDX_TOP - (u64)idx) < T2) return;
         }
         unsigned p = atomicAdd(&st->out_count, 1u);
         if ((i64)p < cap) { out_k1[p] = k1; out_k2[p] = k2; out_idx[p] = idx; }
+    };
+    const i64 tid = (i64)blockIdx.x * blockDim.x + threadIdx.x, nthr = (i64)gridDim.x * blockDim.x;
+    const i64 N8 = a.N & ~(i64)7;
+    for (i64 i = tid * 2; i < N8; i += nthr * 8) {
+        ulonglong2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const i64 j = i + u * nthr * 2;
+            v[u] = (j < N8) ? *reinterpret_cast<const ulonglong2*>(a.key1 + j) : make_ulonglong2(0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const i64 j = i + u * nthr * 2;
+            if (j < N8) { take(j, v[u].x); take(j + 1, v[u].y); }
+        }
     }
+    for (i64 i = N8 + tid; i < a.N; i += nthr) take(i, a.key1[i]);
 }
 
 // rank-counting sort of the m <= cap winners by (k1 desc, k2 desc, idx asc)
