@@ -38,7 +38,11 @@ constexpr int I8_SLOTS = 8;                               // TMEM accumulator ri
 constexpr int I8_A0_BYTES = I8_NS * I8_M * I8_K0;         // 28672: layer-0 A image of a tile
 constexpr int I8_AH_BYTES = I8_NS * I8_M * 64;            // 57344: hidden-layer A image of a tile
 constexpr int I8_AUX_BYTES = I8_M * 16;                   // base[128], max_elem[128]
-constexpr int I8_TILE_BYTES = I8_A0_BYTES + I8_AUX_BYTES; // bytes per tile in the prep buffer
+// Staged tile in global memory (k_prep_i8 -> TMA): compact -- the 16 leading input digits of every row and slice, then
+// the (at most 4) remaining ones as one word, then aux; the zero padding of the K = 32 image is added in shared memory.
+constexpr int I8_G_MAIN = I8_NS * I8_M * 16;              // 14336
+constexpr int I8_G_TAIL = I8_NS * I8_M * 4;               // 3584
+constexpr int I8_TILE_BYTES = I8_G_MAIN + I8_G_TAIL + I8_AUX_BYTES;   // 19968 bytes per tile (156 B per candidate)
 constexpr int I8_W0_BYTES = I8_NS * I8_N * I8_K0;         // 14336
 constexpr int I8_WH_BYTES = I8_NS * I8_N * 64;            // 28672
 constexpr int I8_EPI_WARPS = 16;
@@ -301,16 +305,16 @@ __device__ __forceinline__ uint32_t i8_pack4(unsigned long long u0, unsigned lon
 }
 
 // Write one row (candidate) of a layer-0 tile image: NIN mapminmax'ed inputs -> 7 slices x 32 digit bytes, plus aux.
-// Tile image layout: [slice s (0 = most significant)][k chunk c = k / 16][row][k % 16]; aux: base[128], max_elem[128].
+// Shared-memory image: [slice s (0 = most significant)][k chunk c = k / 16][row][k % 16]; staged tile: see I8_TILE_BYTES.
 template <int NIN>
 __device__ __forceinline__ void i8_store_row(uint8_t* tile, int row, const double (&p)[NIN], double base, double max_elem,
                                              bool valid, int* status)
 {
-    uint32_t w[I8_NS][8];
+    uint32_t w[I8_NS][5];                        // words of 4 input digits: 16 inputs of the first k chunk + inputs 16..19
 #pragma unroll
     for (int s = 0; s < I8_NS; ++s)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) w[s][c] = 0;
+        for (int c = 0; c < 5; ++c) w[s][c] = 0;
     bool bad = false;
 #pragma unroll
     for (int k = 0; k < NIN; ++k) {
@@ -324,13 +328,13 @@ __device__ __forceinline__ void i8_store_row(uint8_t* tile, int row, const doubl
         }
     }
     if (bad && valid) atomicCAS(status, 0, 2);
+    static_assert(NIN <= 20, "the compact tile format keeps one word of the second k chunk");
 #pragma unroll
     for (int s = 0; s < I8_NS; ++s) {
-        uint4* dst = reinterpret_cast<uint4*>(tile + s * (I8_M * I8_K0) + row * 16);
-        dst[0] = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
-        dst[I8_M] = make_uint4(w[s][4], w[s][5], w[s][6], w[s][7]);     // + 2048 bytes: second k chunk
+        *reinterpret_cast<uint4*>(tile + s * (I8_M * 16) + row * 16) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+        *reinterpret_cast<uint32_t*>(tile + I8_G_MAIN + s * (I8_M * 4) + row * 4) = w[s][4];     // inputs 16..19
     }
-    double* aux = reinterpret_cast<double*>(tile + I8_A0_BYTES);
+    double* aux = reinterpret_cast<double*>(tile + I8_G_MAIN + I8_G_TAIL);
     aux[row] = valid ? base : 0.0;
     aux[I8_M + row] = valid ? max_elem : 0.0;
 }
@@ -560,7 +564,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
             mbar_init(B_EMPTY + 8 * i, I8_EPI_WARPS);
         }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(B_A0 + 8 * i, D > 0 ? I8_M / 32 : 1);   // fused: one arrival per 32-row pass; TMA: expect_tx
+            mbar_init(B_A0 + 8 * i, D > 0 ? I8_M / 32 : 2);   // fused: one arrival per 32-row pass; staged: expect_tx + tail
             mbar_init(B_FREE + 8 * i, 1);
             mbar_init(B_ACT + 8 * i, I8_EPI_WARPS);
             mbar_init(B_Y + 8 * i, I8_EPI_WARPS);
@@ -643,14 +647,24 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                 ok = mbar_wait_relaxed(B_FREE + 8 * ln, (cnt & 1) ^ 1, abort_flag, a.status);
                 ok = __all_sync(0xffffffffu, ok);
                 if (!ok) break;
+                const uint8_t* src = a.tiles + tile * (i64)I8_TILE_BYTES;
+                uint8_t* img = sm + L::OFF_A + ln * I8_AH_BYTES;
                 if (elect_one()) {
-                    mbar_expect_tx(B_A0 + 8 * ln, I8_TILE_BYTES);
-                    const uint8_t* src = a.tiles + tile * (i64)I8_TILE_BYTES;
-                    tma_load_1d(smem_u32(sm + L::OFF_A + ln * I8_AH_BYTES), src, I8_A0_BYTES, B_A0 + 8 * ln);
-                    tma_load_1d(smem_u32(sm + L::OFF_AUX + (2 * ln + (cnt & 1)) * I8_AUX_BYTES), src + I8_A0_BYTES, I8_AUX_BYTES,
+                    mbar_expect_tx(B_A0 + 8 * ln, I8_G_MAIN + I8_AUX_BYTES);
+#pragma unroll
+                    for (int sl = 0; sl < I8_NS; ++sl)      // first k chunk of every slice
+                        tma_load_1d(smem_u32(img + sl * (I8_M * I8_K0)), src + sl * (I8_M * 16), I8_M * 16, B_A0 + 8 * ln);
+                    tma_load_1d(smem_u32(sm + L::OFF_AUX + (2 * ln + (cnt & 1)) * I8_AUX_BYTES), src + I8_G_MAIN + I8_G_TAIL, I8_AUX_BYTES,
                                 B_A0 + 8 * ln);
                 }
                 __syncwarp();
+                // second k chunk: one word per row and slice from the staged tile, 12 zero bytes of padding
+                const uint32_t* tail = reinterpret_cast<const uint32_t*>(src + I8_G_MAIN);
+                for (int t = lane; t < I8_NS * I8_M; t += 32)
+                    *reinterpret_cast<uint4*>(img + (t >> 7) * (I8_M * I8_K0) + I8_M * 16 + (t & (I8_M - 1)) * 16) = make_uint4(__ldg(tail + t), 0, 0, 0);
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(B_A0 + 8 * ln);
             }
         }
     } else if (warp == I8_EPI_WARPS) {
