@@ -12,6 +12,14 @@ from . import _capi, cover
 from .cut_select_qp import CutSolver
 
 
+def _row_keys(idx):
+    """(N, dim <= 5) int16 index rows, -1 padded, entries < 511 -> one uint64 key per row."""
+    k = np.zeros(idx.shape[0], dtype=np.uint64)
+    for t in range(idx.shape[1]):
+        k = (k << np.uint64(9)) | (idx[:, t].astype(np.int64) + 1).astype(np.uint64)
+    return k
+
+
 class CutSolverQCQP(CutSolver):
     def __init__(self):
         super(CutSolverQCQP, self).__init__()
@@ -36,11 +44,11 @@ class CutSolverQCQP(CutSolver):
         if agg_obj.is_all:                                   # every element of P(E_m) is in P(E_0)
             self._agg_list = agg_cons
             return empty
-        obj_keys = set(agg_obj.keys())
         cons_idx = agg_cons.idx if not agg_cons.is_all else \
             _capi.unrank(n, dim, np.arange(len(agg_cons))).astype(np.int16)
-        keys = [tuple(int(v) for v in r if v >= 0) for r in cons_idx]
-        inter = np.array([k in obj_keys for k in keys], dtype=bool)
+        # membership of every P(E_m) row in P(E_0): one 45-bit key per (-1 padded) index row instead of the reference's
+        # O(N^2) `el in agg_list` scans (cut_select_qcqp.py:322-331)
+        inter = np.isin(_row_keys(cons_idx), _row_keys(agg_obj.idx))
         self._agg_list = cover.AggList(n, dim, Q_arr, idx=np.ascontiguousarray(cons_idx[inter]))
         return cover.AggList(n, dim, Q_arr, idx=np.ascontiguousarray(cons_idx[~inter]))
 
