@@ -311,21 +311,25 @@ __device__ __forceinline__ void i8_store_row(uint8_t* tile, int row, const doubl
                                              bool valid, int* status)
 {
     uint32_t w[I8_NS][5];                        // words of 4 input digits: 16 inputs of the first k chunk + inputs 16..19
-#pragma unroll
-    for (int s = 0; s < I8_NS; ++s)
-#pragma unroll
-        for (int c = 0; c < 5; ++c) w[s][c] = 0;
     bool bad = false;
 #pragma unroll
-    for (int k = 0; k < NIN; ++k) {
-        const double pk = valid ? p[k] : 0.0;
-        bad |= !(fabs(pk) < 2.0);
-        const unsigned long long u = i8_quantize(pk, 1125899906842624.0 /* 2^50 */);
+    for (int g = 0; g < 5; ++g) {
+        unsigned long long u[4];
 #pragma unroll
-        for (int b = 0; b < I8_NS; ++b) {
-            const uint32_t byte = (uint32_t)(u >> (8 * b)) & 0xFFu;
-            w[6 - b][k >> 2] |= byte << (8 * (k & 3));
+        for (int t = 0; t < 4; ++t) {
+            const int k = 4 * g + t;
+            const double pk = (k < NIN && valid) ? p[k < NIN ? k : 0] : 0.0;
+            if (k < NIN) bad |= !(fabs(pk) < 2.0);
+            u[t] = i8_quantize(pk, 1125899906842624.0 /* 2^50 */);
         }
+        // byte b of the digit word is slice 6 - b (slice 0 = most significant digit)
+        w[6][g] = i8_pack4<0>(u[0], u[1], u[2], u[3]);
+        w[5][g] = i8_pack4<1>(u[0], u[1], u[2], u[3]);
+        w[4][g] = i8_pack4<2>(u[0], u[1], u[2], u[3]);
+        w[3][g] = i8_pack4<3>(u[0], u[1], u[2], u[3]);
+        w[2][g] = i8_pack4<4>(u[0], u[1], u[2], u[3]);
+        w[1][g] = i8_pack4<5>(u[0], u[1], u[2], u[3]);
+        w[0][g] = i8_pack4<6>(u[0], u[1], u[2], u[3]);
     }
     if (bad && valid) atomicCAS(status, 0, 2);
     static_assert(NIN <= 20, "the compact tile format keeps one word of the second k chunk");

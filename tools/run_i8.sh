@@ -1,4 +1,3 @@
 set -x
-timeout 90 python tools/i8_trace.py -q > gpurun_out/i8_trace_cur.log 2>&1; head -3 gpurun_out/i8_trace_cur.log
 timeout 300 python -m pytest tests/test_gpu_nn_i8.py tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -3
 timeout 200 python bench.py --no-cpu-baseline --steps 5 --warmup 3 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('cfg4 ms/step', d['ms_per_step'], 'nn_ms', d['roofline'].get('nn_kernels_ms'), d['roofline']['frac'], d['selection'])"
