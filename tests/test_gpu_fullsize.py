@@ -104,3 +104,24 @@ def test_whole_cover_selection_properties(capi, blobs, inst, rho):
     sets = capi.unrank(n, rho, r1["idx"])
     lam_o, _ = orc.score_cover(Q_arr, n, sets, np.full(k, rho), vv, blobs, want_obj=False)
     assert np.abs(-lam_o - r1["score"]).max() < LAM_TOL
+
+
+def test_n250_ranks_beyond_32_bits(capi, blobs):
+    """n = 250 (the largest instances of the reference), rho = 5: C(250,5) = 7,817,031,300 > 2^32; windows at the far end
+    and in the middle of the rank space against the oracle (64-bit unranking, gathers over the 251 KB instance arrays)."""
+    n, rho = 250, 5
+    Q_arr, adj = orc.boxqp_arrays(orc.synth_instance(n, 0.5, seed=17))
+    vv = orc.synth_point(n, seed=18)
+    N = capi.binom(n, rho)
+    assert N == 7817031300
+    eng = _engine(capi, blobs, n, Q_arr, rho)
+    for r0, r1 in ((N - 30001, N), (5000000000, 5000020000)):
+        idx = orc.cover_all_window(n, rho, r0, r1)
+        assert np.array_equal(idx, capi.unrank(n, rho, np.arange(r0, r1)))
+        lam_o, obj_o = orc.score_cover(Q_arr, n, idx, np.full(r1 - r0, rho), vv, blobs)
+        eng.set_cover_all(rho, r0, r1)
+        r = eng.select(4, vv, 300)
+        lam, obj = eng.scores()
+        assert np.abs(lam - lam_o).max() < LAM_TOL and np.abs(obj - obj_o).max() < OBJ_TOL
+        ns, order, score = orc.select_comb(obj_o, lam_o, 300)
+        assert r["new_strat"] == ns and np.array_equal(r["idx"] - r0, order[:300])
