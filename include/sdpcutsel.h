@@ -125,6 +125,12 @@ int sdpcs_scores(sdpcs_ctx *ctx, int64_t i0, int64_t i1, double *out_lam, double
  * out[2] = #strong (obj > thres_min_opt and violated).  (cut_select_qp.py:604-615, 629) */
 int sdpcs_counts(sdpcs_ctx *ctx, int64_t *out3);
 
+/* Largest obj among the candidates with obj > thres_min_opt that are NOT violated, as seen by the last sdpcs_topk pass
+ * (-inf if none).  With it a sharded caller can tell when the combined rule (cut_select_qp.py:603-625) reduces to the
+ * strong list itself: n_strong >= k and max - big_m < pivot_obj + big_m (every one of the k strong elements up to the
+ * pivot is re-scored obj + big_m, nothing else can reach them), so that the second selection pass can be skipped. */
+int sdpcs_max_pos_nonviolated(sdpcs_ctx *ctx, double *out);
+
 /* Top-k of the resident scores.  mode:
  *   1  feasibility: violated only, key -lam desc, ties agg_idx asc          (cut_select_qp.py:639-654)
  *   2  optimality:  all, key obj desc, ties agg_idx asc                      (cut_select_qp.py:599-601)

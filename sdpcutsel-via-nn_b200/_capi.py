@@ -20,7 +20,7 @@ EXPORTS = [
     "sdpcs_num_candidates", "sdpcs_score", "sdpcs_scores", "sdpcs_counts", "sdpcs_topk", "sdpcs_merge_topk",
     "sdpcs_select", "sdpcs_unrank", "sdpcs_binom", "sdpcs_gen_cuts", "sdpcs_eigendecomp", "sdpcs_set_tri_pattern",
     "sdpcs_triangles", "sdpcs_nn_eval", "sdpcs_nn_debug_layer", "sdpcs_fp64_peak",
-    "sdpcs_set_cover_pattern", "sdpcs_get_cover_rows", "sdpcs_gen_cuts_csr", "sdpcs_triangle_rows_csr", "sdpcs_dense_eigcuts",
+    "sdpcs_set_cover_pattern", "sdpcs_get_cover_rows", "sdpcs_gen_cuts_csr", "sdpcs_triangle_rows_csr", "sdpcs_dense_eigcuts", "sdpcs_max_pos_nonviolated",
 ]
 
 NN_TCGEN05, NN_DMMA = 0, 1
@@ -83,6 +83,7 @@ class Engine(object):
             self._ctx = None
             raise SdpcsError("sdpcs_create failed (%d): %s" % (rc, msg.decode() if msg else ""))
         self.n = 0
+        self.big_m = 1000.0            # sdpcs_default_params
         self.rho = 0
         self.device = device
 
@@ -112,6 +113,7 @@ class Engine(object):
         for k, v in kw.items():
             setattr(p, k, v)
         self._ck(self._lib.sdpcs_set_params(self._ctx, ctypes.byref(p)))
+        self.big_m = float(p.big_m)
 
     def set_weights(self, rho, blob):
         blob = _f64(blob)
@@ -189,6 +191,11 @@ class Engine(object):
                                       _ptr(idx), _ptr(sc), _ptr(lam), _ptr(obj), ctypes.byref(n)))
         m = n.value
         return idx[:m], sc[:m], lam[:m], obj[:m]
+
+    def max_pos_nonviolated(self):
+        out = c_dbl()
+        self._ck(self._lib.sdpcs_max_pos_nonviolated(self._ctx, ctypes.byref(out)))
+        return out.value
 
     def merge_topk(self, score, obj2, idx, k):
         score, idx = _f64(score), np.ascontiguousarray(idx, dtype=np.int64)

@@ -60,6 +60,7 @@ struct sdpcs_ctx {
     void* h_out = nullptr;         // pinned download staging
     size_t h_out_bytes = 0;
     i64 last_counts[3] = {0, 0, 0};
+    double last_max_pos_nonviol = -INFINITY;   // largest obj among (obj > thres_min_opt and not violated), last top-k pass
     // triangles
     uint8_t* d_adj = nullptr;
     bool have_adj = false;
@@ -902,6 +903,7 @@ static int download_topk(sdpcs_ctx* ctx, i64 k, int64_t* out_idx, double* out_sc
     const SelState* st = (const SelState*)h;
     i64 m = k > 0 ? std::min<i64>((i64)st->out_count, k) : 0;
     ctx->last_counts[0] = ctx->N; ctx->last_counts[1] = st->n_violated; ctx->last_counts[2] = st->n_strong;
+    ctx->last_max_pos_nonviol = st->max_pos_nonviol ? dec_key(st->max_pos_nonviol) : -INFINITY;
     if (out_n) *out_n = m;
     if (out_idx) memcpy(out_idx, h + sizeof(SelState), m * 8);
     if (out_score) memcpy(out_score, h + sizeof(SelState) + kb, m * 8);
@@ -925,6 +927,28 @@ extern "C" int sdpcs_counts(sdpcs_ctx* ctx, int64_t* out3)
 {
     if (!ctx || !out3) return SDPCS_ERR_INVALID;
     out3[0] = ctx->last_counts[0]; out3[1] = ctx->last_counts[1]; out3[2] = ctx->last_counts[2];
+    return SDPCS_OK;
+}
+
+// Combined rule (cut_select_qp.py:603-625), shortcut: when the strong set S = {obj > 0 and violated} has at least k
+// elements, the walk stops at the k-th of them (the pivot).  The k strong elements up to the pivot are re-scored obj + big_m;
+// every other candidate keeps obj <= pivot_obj (not walked) or gets obj - big_m (walked, not violated).  If even the
+// largest such obj - big_m stays strictly below pivot_obj + big_m, the re-sorted list starts with exactly those k elements
+// in (obj desc, idx asc) order -- the list pass 1 already produced -- and the second selection pass is not needed.
+static bool combined_is_strong_prefix(double big_m, bool all_walked, i64 k, double pivot_obj, double max_pos_nonviol)
+{
+    if (all_walked || k <= 0 || !(big_m > 0.0)) return false;
+    const double floor_top = pivot_obj + big_m;                       // smallest re-scored strong element
+    if (!(pivot_obj < floor_top)) return false;                       // overflow / absorption: take the general path
+    return max_pos_nonviol == -INFINITY || (max_pos_nonviol - big_m) < floor_top;
+}
+
+// largest obj among candidates with obj > thres_min_opt that are not violated, as seen by the last sdpcs_topk pass
+// (-inf if there is none): lets a sharded caller apply the same shortcut on the merged lists
+extern "C" int sdpcs_max_pos_nonviolated(sdpcs_ctx* ctx, double* out)
+{
+    if (!ctx || !out) return SDPCS_ERR_INVALID;
+    *out = ctx->last_max_pos_nonviol;
     return SDPCS_OK;
 }
 
@@ -959,13 +983,26 @@ extern "C" int sdpcs_select(sdpcs_ctx* ctx, int strat, const double* vars_values
         const bool all_walked = n_strong_total < k || k == 0;
         const double pobj = all_walked ? 0.0 : sobj[k - 1];
         const i64 pidx = all_walked ? 0 : sidx[k - 1];
-        float ms1 = 0;
+        float ms1 = 0, ms2 = 0;
         cudaEventElapsedTime(&ms1, ctx->ev[2], ctx->ev[3]);
-        // pass 2: final measure of cut_select_qp.py:603-625
-        if ((rc = topk_device(ctx, 4, k, pobj, pidx, all_walked ? 1 : 0))) return rc;
-        if ((rc = download_topk(ctx, k, out_idx, out_score, out_lam, out_obj, out_n))) return rc;
-        float ms2 = 0;
-        cudaEventElapsedTime(&ms2, ctx->ev[2], ctx->ev[3]);
+        if (combined_is_strong_prefix(ctx->params.big_m, all_walked, k, pobj, ctx->last_max_pos_nonviol)) {
+            // the k strong elements up to the pivot get +big_m and nothing else can reach them: the final list IS the
+            // strong list of pass 1 in its own order (ties after the addition fall back to obj desc, idx asc)
+            if (out_n) *out_n = ns;
+            const char* h = (const char*)ctx->h_out;
+            const size_t kb = (size_t)std::max<i64>(k, 1) * 8;
+            for (i64 i = 0; i < ns; ++i) {
+                if (out_idx) out_idx[i] = sidx[i];
+                if (out_score) out_score[i] = sobj[i] + ctx->params.big_m;
+            }
+            if (out_lam) memcpy(out_lam, h + sizeof(SelState) + 2 * kb, ns * 8);
+            if (out_obj) memcpy(out_obj, h + sizeof(SelState) + 3 * kb, ns * 8);
+        } else {
+            // pass 2: final measure of cut_select_qp.py:603-625
+            if ((rc = topk_device(ctx, 4, k, pobj, pidx, all_walked ? 1 : 0))) return rc;
+            if ((rc = download_topk(ctx, k, out_idx, out_score, out_lam, out_obj, out_n))) return rc;
+            cudaEventElapsedTime(&ms2, ctx->ev[2], ctx->ev[3]);
+        }
         ctx->tm.select_ms = ms1 + ms2;
         ctx->ev_select = false;
         const i64 strong = std::min<i64>(n_strong_total, k);

@@ -23,6 +23,7 @@ struct SelState {
     i64 k_eff;       // min(k, n_valid)
     i64 n_violated;  // counters filled by k_make_keys
     i64 n_strong;
+    u64 max_pos_nonviol; // enc_key of the largest obj among candidates with obj > thres_min_opt that are NOT violated (0: none)
     int level;
     int done;
     unsigned out_count;
@@ -45,10 +46,12 @@ struct KeyArgs {
 __global__ void __launch_bounds__(256) k_make_keys(KeyArgs a)
 {
     i64 nv = 0, ns = 0;
+    u64 mx = 0;
     auto make = [&](i64 i, double lam, double obj, u64& k1, u64& k2) {
         bool viol = a.lam && lam < a.thr_eig;
         bool pos = a.obj && obj > a.thr_opt;
         nv += viol; ns += (viol && pos);
+        if (pos && !viol) { const u64 e = enc_key(obj); mx = e > mx ? e : mx; }
         k1 = 0; k2 = 0;
         switch (a.mode) {
         case 1: k1 = viol ? enc_key(-lam) : 0; break;
@@ -97,7 +100,12 @@ __global__ void __launch_bounds__(256) k_make_keys(KeyArgs a)
     }
     // block reduce the two counters
     __shared__ i64 sh[2][8];
-    for (int o = 16; o; o >>= 1) { nv += __shfl_xor_sync(0xffffffffu, nv, o); ns += __shfl_xor_sync(0xffffffffu, ns, o); }
+    for (int o = 16; o; o >>= 1) {
+        nv += __shfl_xor_sync(0xffffffffu, nv, o); ns += __shfl_xor_sync(0xffffffffu, ns, o);
+        const u64 m2 = __shfl_xor_sync(0xffffffffu, mx, o);
+        mx = m2 > mx ? m2 : mx;
+    }
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax((unsigned long long*)&a.st->max_pos_nonviol, (unsigned long long)mx);
     if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = nv; sh[1][threadIdx.x >> 5] = ns; }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -113,7 +121,7 @@ __global__ void k_sel_reset(SelState* st)
     for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x) st->hist[i] = 0;
     if (threadIdx.x == 0) {
         st->T[0] = st->T[1] = st->T[2] = 0; st->prefix = 0; st->need = 0; st->n_valid = 0; st->k_eff = 0;
-        st->n_violated = 0; st->n_strong = 0; st->level = 0; st->done = 0; st->out_count = 0;
+        st->n_violated = 0; st->n_strong = 0; st->max_pos_nonviol = 0; st->level = 0; st->done = 0; st->out_count = 0;
     }
 }
 

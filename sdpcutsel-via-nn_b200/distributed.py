@@ -57,31 +57,34 @@ class ShardedSelector(object):
         self.dist.all_reduce(t, group=self.group)
         return t.cpu().numpy()
 
-    def _gather_merge(self, k, idx, score, lam, obj, use_obj2, counts=None):
-        """All-gather of the local lists (k + 1 rows of 4 doubles per rank) and the identical merge on every rank.
+    def _gather_merge(self, k, idx, score, lam, obj, use_obj2, counts=None, extra=0.0):
+        """All-gather of the local lists (k + 2 rows of 4 doubles per rank) and the identical merge on every rank.
         Row 0 carries the list length and, when given, the rank's three counters (they ride along instead of needing
-        their own all-reduce); returns (idx, score, lam, obj, summed counters or None)."""
+        their own all-reduce), row 1 one more statistic (`extra`, reduced with max); returns (idx, score, lam, obj,
+        summed counters or None, max of extra)."""
         m = idx.shape[0]
-        pack = np.zeros((k + 1, 4))
+        pack = np.zeros((k + 2, 4))
         pack[0, 0] = m
         if counts is not None:
             pack[0, 1:4] = counts          # < 2^44: exact in float64
-        pack[1:m + 1, 0] = idx            # agg_idx < 2^44: exact in float64
-        pack[1:m + 1, 1] = score
-        pack[1:m + 1, 2] = lam
-        pack[1:m + 1, 3] = obj
+        pack[1, 0] = extra
+        pack[2:m + 2, 0] = idx            # agg_idx < 2^44: exact in float64
+        pack[2:m + 2, 1] = score
+        pack[2:m + 2, 2] = lam
+        pack[2:m + 2, 3] = obj
         allp = self._allgather(pack)
         tot = allp[:, 0, 1:4].sum(axis=0).astype(np.int64) if counts is not None else None
-        rows = np.concatenate([allp[r, 1:int(allp[r, 0, 0]) + 1] for r in range(self.world)], axis=0)
+        ext = float(allp[:, 1, 0].max())
+        rows = np.concatenate([allp[r, 2:int(allp[r, 0, 0]) + 2] for r in range(self.world)], axis=0)
         if rows.shape[0] == 0:
             z = np.zeros(0)
-            return z.astype(np.int64), z, z, z, tot
+            return z.astype(np.int64), z, z, z, tot, ext
         gidx = rows[:, 0].astype(np.int64)
         if self.world == 1:
             perm = np.arange(min(k, rows.shape[0]))
         else:
             perm = self.eng.merge_topk(rows[:, 1], rows[:, 3] if use_obj2 else None, gidx, k)
-        return gidx[perm], rows[perm, 1], rows[perm, 2], rows[perm, 3], tot
+        return gidx[perm], rows[perm, 1], rows[perm, 2], rows[perm, 3], tot, ext
 
     # -- public ------------------------------------------------------------------------------------
     def select(self, strat, vars_values, k, n_total=None):
@@ -96,26 +99,33 @@ class ShardedSelector(object):
         if strat != 4:
             idx, sc, lam, obj = eng.topk(strat, k)
             t = self._t("score+topk", t)
-            gi, gs, gl, go, counts = self._gather_merge(k, idx, sc, lam, obj, False, eng.counts())
+            gi, gs, gl, go, counts, _ = self._gather_merge(k, idx, sc, lam, obj, False, eng.counts())
             self._t("exchange+merge", t)
             return dict(idx=gi, score=gs, lam=gl, obj=go, counts=counts, new_strat=strat)
         idx, sc, lam, obj = eng.topk(3, k)
         t = self._t("score+topk1", t)
         # the pivot of the combined rule needs k <= N; N is only known after the exchange, so gather k rows and cut after
-        si, ss, _, so, counts = self._gather_merge(k, idx, sc, lam, obj, False, eng.counts())
+        mpn = eng.max_pos_nonviolated() if hasattr(eng, "max_pos_nonviolated") else np.inf
+        si, ss, sl, so, counts, mpn = self._gather_merge(k, idx, sc, lam, obj, False, eng.counts(), mpn)
         N, n_viol, n_strong = (int(v) for v in counts)
         k = min(k, N)
-        si, so = si[:k], so[:k]
+        si, sl, so = si[:k], sl[:k], so[:k]
         t = self._t("gather+merge1", t)
         all_walked = n_strong < k or k == 0
         pobj, pidx = (0.0, 0) if all_walked else (float(so[k - 1]), int(si[k - 1]))
-        idx, sc, lam, obj = eng.topk(4, k, pobj, pidx, 1 if all_walked else 0)
-        t = self._t("topk2", t)
-        gi, gs, gl, go, _ = self._gather_merge(k, idx, sc, lam, obj, True)
-        self._t("gather+merge2", t)
+        big_m = float(getattr(eng, "big_m", 1000.0))
         strong = min(n_strong, k)
         viol_walked = n_viol if all_walked else k
         new_strat = 4
         if k > 0 and N > 0:
             new_strat = 1 if strong / k < viol_walked / N else 4
-        return dict(idx=gi, score=gs, lam=gl, obj=go, counts=np.array([N, viol_walked, strong]), new_strat=new_strat)
+        counts = np.array([N, viol_walked, strong])
+        if not all_walked and big_m > 0 and pobj < pobj + big_m and mpn - big_m < pobj + big_m:
+            # the k strong elements up to the pivot are re-scored obj + big_m and nothing else can reach them
+            # (combined_is_strong_prefix in capi.cu): the merged strong list is the answer, no second pass
+            return dict(idx=si, score=so + big_m, lam=sl, obj=so, counts=counts, new_strat=new_strat)
+        idx, sc, lam, obj = eng.topk(4, k, pobj, pidx, 1 if all_walked else 0)
+        t = self._t("topk2", t)
+        gi, gs, gl, go, _, _ = self._gather_merge(k, idx, sc, lam, obj, True)
+        self._t("gather+merge2", t)
+        return dict(idx=gi, score=gs, lam=gl, obj=go, counts=counts, new_strat=new_strat)

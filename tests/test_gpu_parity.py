@@ -301,3 +301,56 @@ def test_merge_topk_sorted_runs_and_unsorted_input(capi):
     # unsorted input
     score, idx = rng.normal(size=3000), rng.permutation(3000).astype(np.int64)
     assert np.array_equal(eng.merge_topk(score, None, idx, 100), np.argsort(-score, kind="stable")[:100])
+
+
+def test_combined_rule_shortcut_and_general_path(capi, blobs):
+    """sdpcs_select strat 4: when the strong set has >= k elements and no non-violated candidate comes within 2 big_m of
+    the pivot, the strong list of pass 1 is returned directly; with a tiny big_m the condition fails and the two-pass
+    path runs.  Both must equal the oracle's literal walk (cut_select_qp.py:601-630), scores included."""
+    n, rho = 26, 4
+    Q_arr, adj = orc.boxqp_arrays(orc.synth_instance(n, 0.75, seed=31))
+    vv = orc.synth_point(n, seed=32)
+    idx = orc.cover_all(n, rho)
+    lam_o, obj_o = orc.score_cover(Q_arr, n, idx, np.full(idx.shape[0], rho), vv, blobs)
+    for k in (1, 50, 700, idx.shape[0]):
+        ns, order, score = orc.select_comb_walk(obj_o, lam_o, k)
+        eng = make_engine(capi, blobs, n, Q_arr, rhos=(rho,))
+        eng.set_cover_all(rho)
+        r = eng.select(4, vv, k)
+        assert r["new_strat"] == ns and np.array_equal(r["idx"], order[:k])
+        assert np.abs(r["score"] - score[:k]).max() < OBJ_TOL
+        assert np.abs(r["lam"] - lam_o[r["idx"]]).max() < LAM_TOL and np.abs(r["obj"] - obj_o[r["idx"]]).max() < OBJ_TOL
+    # A point between the random one and a PSD one: some candidates with obj > 0 are NOT violated.  With big_m = 1000 the
+    # shortcut still applies (oracle walk), with a tiny big_m the non-violated ones overtake: general two-pass path,
+    # compared with a restatement of the rule.
+    nb = n * (n + 1) // 2
+    x, iu = vv[nb:], np.triu_indices(n)
+    Xr = np.zeros((n, n))
+    Xr[iu] = vv[:nb]
+    Xp = np.outer(x, x) + np.diag(np.full(n, 0.2))
+    v2 = np.concatenate([(0.1 * Xp + 0.9 * (Xr + np.triu(Xr, 1).T))[iu], x])
+    lam_o, obj_o = orc.score_cover(Q_arr, n, idx, np.full(idx.shape[0], rho), v2, blobs)
+    strong_o = (obj_o > 0) & (lam_o < -1e-15)
+    k = int(strong_o.sum())                       # the pivot is the weakest strong element
+    assert k >= 5 and ((obj_o > 0) & ~(lam_o < -1e-15)).any()
+    eng = make_engine(capi, blobs, n, Q_arr, rhos=(rho,))
+    eng.set_cover_all(rho)
+    ns, order, score = orc.select_comb_walk(obj_o, lam_o, k)
+    r = eng.select(4, v2, k)
+    assert r["new_strat"] == ns and np.array_equal(r["idx"], order[:k]) and np.abs(r["score"] - score[:k]).max() < OBJ_TOL
+    eng.set_params(big_m=1e-3)
+    r = eng.select(4, v2, k)
+    lam, obj = eng.scores()
+    o = np.argsort(-obj, kind="stable")
+    viol = lam[o] < -1e-15
+    strong = (obj[o] > 0) & viol
+    pivot = np.nonzero(np.cumsum(strong) == k)[0][0]
+    f = obj[o].copy()
+    w = np.arange(o.size) <= pivot
+    f[w & strong] += 1e-3
+    f[w & (obj[o] > 0) & ~viol] -= 1e-3
+    want = o[np.argsort(-f, kind="stable")][:k]
+    assert np.array_equal(r["idx"], want)
+    nonviol_pos = (obj > 0) & ~(lam < -1e-15)
+    assert obj[nonviol_pos].max() - 1e-3 >= obj[o][pivot] + 1e-3          # the shortcut condition does not hold here ...
+    assert not np.array_equal(np.sort(want), np.sort(o[np.nonzero(strong)[0][:k]]))   # ... and it would have been wrong

@@ -16,9 +16,15 @@ N_VARS, RHO, K = 14, 3, 40
 class FakeEngine(object):
     """Numpy stand-in with the Engine methods ShardedSelector uses (score / topk / counts / merge_topk)."""
 
+    big_m = 1000.0
+
     def __init__(self, lam, obj, base):
         self.lam, self.obj, self.base = lam, obj, base
         self._counts = np.zeros(3, dtype=np.int64)
+
+    def max_pos_nonviolated(self):
+        m = (self.obj > 0) & ~(self.lam < -1e-15)
+        return float(self.obj[m].max()) if m.any() else -np.inf
 
     def score(self, vars_values, want):
         pass
@@ -55,7 +61,7 @@ class FakeEngine(object):
         return np.lexsort((idx, -obj2, -score))[:k]
 
 
-def _scores():
+def _scores(huge=False):
     Q_arr, adj = orc.boxqp_arrays(orc.synth_instance(N_VARS, 0.8, seed=7))
     vv = orc.synth_point(N_VARS, seed=8)
     idx = orc.cover_all(N_VARS, RHO)
@@ -63,6 +69,8 @@ def _scores():
     rng = np.random.default_rng(5)
     obj = rng.normal(size=lam.size)          # any scores do: only the plumbing is under test
     obj[::7] = obj[3]                        # exact ties across shard boundaries
+    if huge:                                 # a non-violated candidate whose obj - 1000 still beats the strong ones:
+        obj[np.nonzero(~(lam < -1e-15))[0][5]] = 5000.0      # the shortcut of the combined rule must not be taken
     return lam, obj
 
 
@@ -71,14 +79,15 @@ def _worker(rank, world, port, ret):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import sdpcutsel_via_nn_b200 as pkg
-    lam, obj = _scores()
-    N = lam.size
-    r0, r1 = pkg.distributed.shard_range(N, world, rank)
-    sel = pkg.distributed.ShardedSelector(FakeEngine(lam[r0:r1], obj[r0:r1], r0))
     out = {}
-    for strat, k in ((1, K), (2, K), (4, K), (4, 10 * K)):
-        r = sel.select(strat, None, k)
-        out[(strat, k)] = (r["idx"].tolist(), r["score"].tolist(), int(r["new_strat"]), [int(v) for v in r["counts"]])
+    for huge in (False, True):
+        lam, obj = _scores(huge)
+        N = lam.size
+        r0, r1 = pkg.distributed.shard_range(N, world, rank)
+        sel = pkg.distributed.ShardedSelector(FakeEngine(lam[r0:r1], obj[r0:r1], r0))
+        for strat, k in ((1, K), (2, K), (4, K), (4, 10 * K)):
+            r = sel.select(strat, None, k)
+            out[(strat, k, huge)] = (r["idx"].tolist(), r["score"].tolist(), int(r["new_strat"]), [int(v) for v in r["counts"]])
     ret[rank] = out
     dist.barrier()
     dist.destroy_process_group()
@@ -97,19 +106,20 @@ def test_sharded_selection_matches_single_shard():
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
-    lam, obj = _scores()
     assert ret[0] == ret[1]                                    # identical global selection on every rank
-    order, score = orc.select_feas(lam)
-    assert ret[0][(1, K)][0] == order[:K].tolist() and ret[0][(1, K)][1] == score[:K].tolist()
-    order, score = orc.select_opt(obj)
-    assert ret[0][(2, K)][0] == order[:K].tolist()
-    for k in (K, 10 * K):
-        kk = min(k, lam.size)
-        ns, order, score = orc.select_comb(obj, lam, kk)
-        ns2, order2, score2 = orc.select_comb_walk(obj, lam, kk)
-        assert ns == ns2 and np.array_equal(order, order2)
-        got = ret[0][(4, k)]
-        assert got[0] == order[:kk].tolist() and got[1] == score[:kk].tolist() and got[2] == ns
+    for huge in (False, True):                                 # huge: the general two-pass path of the combined rule
+        lam, obj = _scores(huge)
+        order, score = orc.select_feas(lam)
+        assert ret[0][(1, K, huge)][0] == order[:K].tolist() and ret[0][(1, K, huge)][1] == score[:K].tolist()
+        order, score = orc.select_opt(obj)
+        assert ret[0][(2, K, huge)][0] == order[:K].tolist()
+        for k in (K, 10 * K):
+            kk = min(k, lam.size)
+            ns, order, score = orc.select_comb(obj, lam, kk)
+            ns2, order2, score2 = orc.select_comb_walk(obj, lam, kk)
+            assert ns == ns2 and np.array_equal(order, order2)
+            got = ret[0][(4, k, huge)]
+            assert got[0] == order[:kk].tolist() and got[1] == score[:kk].tolist() and got[2] == ns
 
 
 def test_shard_ranges_partition():
