@@ -109,6 +109,12 @@ int sdpcs_set_cover_pattern(sdpcs_ctx *ctx, int rho, const uint8_t *adj, int64_t
  * candidate order: the index tuples the reference keeps in agg_list[i][0] (cut_select_qp.py:525-540). */
 int sdpcs_get_cover_rows(sdpcs_ctx *ctx, int16_t *out_idx, int64_t cap_rows);
 
+/* Multi-GPU sharding of any cover: keep the candidates [begin, end) of the cover as currently set (local
+ * candidate indices); their agg_idx does not change.  For the all-subsets cover this moves the rank range, for a list
+ * cover (built or shipped in full on every rank) it narrows a view, nothing is copied.  A list cover can be restricted
+ * once; set it again to choose another shard. */
+int sdpcs_cover_restrict(sdpcs_ctx *ctx, int64_t begin, int64_t end);
+
 int sdpcs_num_candidates(const sdpcs_ctx *ctx, int64_t *N);
 
 /* Score every candidate of the cover at the LP point vars_values = [X upper-tri row-major | x]

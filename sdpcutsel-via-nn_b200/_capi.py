@@ -20,7 +20,7 @@ EXPORTS = [
     "sdpcs_num_candidates", "sdpcs_score", "sdpcs_scores", "sdpcs_counts", "sdpcs_topk", "sdpcs_merge_topk",
     "sdpcs_select", "sdpcs_unrank", "sdpcs_binom", "sdpcs_gen_cuts", "sdpcs_eigendecomp", "sdpcs_set_tri_pattern",
     "sdpcs_triangles", "sdpcs_nn_eval", "sdpcs_nn_debug_layer", "sdpcs_fp64_peak",
-    "sdpcs_set_cover_pattern", "sdpcs_get_cover_rows", "sdpcs_gen_cuts_csr", "sdpcs_triangle_rows_csr", "sdpcs_dense_eigcuts", "sdpcs_max_pos_nonviolated",
+    "sdpcs_set_cover_pattern", "sdpcs_get_cover_rows", "sdpcs_cover_restrict", "sdpcs_gen_cuts_csr", "sdpcs_triangle_rows_csr", "sdpcs_dense_eigcuts", "sdpcs_max_pos_nonviolated",
 ]
 
 NN_TCGEN05, NN_DMMA = 0, 1
@@ -144,6 +144,10 @@ class Engine(object):
         self._ck(self._lib.sdpcs_set_cover_pattern(self._ctx, c_int(rho), _ptr(adj), c_i64(agg_offset), ctypes.byref(N)))
         self.rho = rho
         return N.value
+
+    def cover_restrict(self, begin, end):
+        """Keep the candidates [begin, end) of the current cover (this rank's shard); agg_idx values are unchanged."""
+        self._ck(self._lib.sdpcs_cover_restrict(self._ctx, c_i64(begin), c_i64(end)))
 
     def cover_rows(self):
         """The current list cover as (N, rho) int16 rows padded with -1 (agg_list[i][0] of the reference)."""

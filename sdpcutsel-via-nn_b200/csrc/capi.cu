@@ -45,6 +45,8 @@ struct sdpcs_ctx {
     uint8_t* d_idx[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     i64* d_pos[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     i64 Nd[6] = {0, 0, 0, 0, 0, 0};
+    i64 lo[6] = {0, 0, 0, 0, 0, 0};    // list cover restricted to a shard (sdpcs_cover_restrict): first row of the view per size class
+    bool restricted = false;
     // scores
     double *d_lam = nullptr, *d_obj = nullptr;
     i64 score_cap = 0;
@@ -466,6 +468,7 @@ extern "C" int sdpcs_set_cover_list(sdpcs_ctx* ctx, int rho, const int16_t* idx,
         pos[d].push_back(i);
     }
     for (int d = 2; d <= 5; ++d) {
+        ctx->lo[d] = 0; ctx->restricted = false;
         if (ctx->d_idx[d]) { cudaFree(ctx->d_idx[d]); ctx->d_idx[d] = nullptr; }
         if (ctx->d_pos[d]) { cudaFree(ctx->d_pos[d]); ctx->d_pos[d] = nullptr; }
         ctx->Nd[d] = (i64)pos[d].size();
@@ -505,6 +508,7 @@ extern "C" int sdpcs_set_cover_pattern(sdpcs_ctx* ctx, int rho, const uint8_t* a
             if (masks[i].w[j >> 6] >> (j & 63) & 1) { edges.push_back(i); edges.push_back(j); }
     const i64 E = (i64)edges.size() / 2;
     for (int d = 2; d <= 5; ++d) {
+        ctx->lo[d] = 0; ctx->restricted = false;
         if (ctx->d_idx[d]) { cudaFree(ctx->d_idx[d]); ctx->d_idx[d] = nullptr; }
         if (ctx->d_pos[d]) { cudaFree(ctx->d_pos[d]); ctx->d_pos[d] = nullptr; }
         ctx->Nd[d] = 0;
@@ -579,11 +583,50 @@ extern "C" int sdpcs_get_cover_rows(sdpcs_ctx* ctx, int16_t* out_idx, int64_t ca
     for (int d = 2; d <= ctx->rho; ++d) {
         if (!ctx->Nd[d]) continue;
         const unsigned grid = (unsigned)std::min<i64>((ctx->Nd[d] + 255) / 256, (i64)ctx->sms * 8);
-        k_cover_rows<<<grid, 256, 0, ctx->stream>>>(ctx->d_idx[d], ctx->d_pos[d], ctx->Nd[d], d, ctx->rho, d_rows);
+        k_cover_rows<<<grid, 256, 0, ctx->stream>>>(ctx->d_idx[d] + ctx->lo[d] * d, ctx->d_pos[d] + ctx->lo[d], ctx->Nd[d], d, ctx->rho, d_rows);
         CU(cudaGetLastError());
     }
     CU(cudaMemcpyAsync(out_idx, d_rows, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    return SDPCS_OK;
+}
+
+// Shard of the current cover: keep the candidates [begin, end) (local indices of the cover as set).  All-subsets covers
+// just move their rank range; list covers keep their device arrays and narrow a view per size class (positions are
+// ascending inside a class).  agg_idx of the survivors is unchanged.
+extern "C" int sdpcs_cover_restrict(sdpcs_ctx* ctx, int64_t begin, int64_t end)
+{
+    if (!ctx) return SDPCS_ERR_INVALID;
+    if (!ctx->mode) return ctx->fail(SDPCS_ERR_STATE, "cover not set");
+    if (begin < 0 || end < begin || end > ctx->N) return ctx->fail(SDPCS_ERR_INVALID, "bad shard range");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->have = 0;
+    if (ctx->mode == 1) {
+        ctx->base += begin; ctx->N = end - begin;
+        return SDPCS_OK;
+    }
+    if (ctx->restricted) return ctx->fail(SDPCS_ERR_STATE, "list cover already restricted: set the cover again first");
+    int rc = ensure_scratch(ctx, 8 * sizeof(i64));
+    if (rc) return rc;
+    i64* d_b = static_cast<i64*>(ctx->d_scratch);
+    for (int d = 2; d <= 5; ++d)
+        if (ctx->Nd[d]) k_pos_bounds<<<1, 1, 0, ctx->stream>>>(ctx->d_pos[d], ctx->Nd[d], begin, end, d_b + 2 * (d - 2));
+    i64 b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    CU(cudaMemcpyAsync(b, d_b, sizeof(b), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int d = 2; d <= 5; ++d) {
+        if (!ctx->Nd[d]) continue;
+        ctx->lo[d] = b[2 * (d - 2)];
+        ctx->Nd[d] = b[2 * (d - 2) + 1] - b[2 * (d - 2)];
+        if (ctx->Nd[d] && begin) {
+            const unsigned grid = (unsigned)std::min<i64>((ctx->Nd[d] + 255) / 256, (i64)ctx->sms * 8);
+            k_pos_shift<<<grid, 256, 0, ctx->stream>>>(ctx->d_pos[d] + ctx->lo[d], ctx->Nd[d], begin);
+        }
+    }
+    CU(cudaGetLastError());
+    ctx->restricted = true;
+    ctx->base += begin; ctx->N = end - begin;
     return SDPCS_OK;
 }
 
@@ -745,7 +788,7 @@ static int score_device(sdpcs_ctx* ctx, int want)
         if (ctx->mode == 1) rc = launch_score_d(ctx, ctx->rho, bit, nullptr, nullptr, ctx->N, ctx->base);
         else
             for (int d = 2; d <= ctx->rho && rc == SDPCS_OK; ++d)
-                rc = launch_score_d(ctx, d, bit, ctx->d_idx[d], ctx->d_pos[d], ctx->Nd[d], 0);
+                rc = launch_score_d(ctx, d, bit, ctx->d_idx[d] + ctx->lo[d] * d, ctx->d_pos[d] + ctx->lo[d], ctx->Nd[d], 0);
         if (bit == 2 && rc == SDPCS_OK) { CU(cudaEventRecord(ctx->ev[7], ctx->stream)); ctx->ev_nn = true; }
     }
     if (rc) return rc;
@@ -766,7 +809,7 @@ static int score_device(sdpcs_ctx* ctx, int want)
             if (ctx->mode == 1) rc = launch_score_d(ctx, ctx->rho, 2, nullptr, nullptr, ctx->N, ctx->base);
             else
                 for (int d = 2; d <= ctx->rho && rc == SDPCS_OK; ++d)
-                    rc = launch_score_d(ctx, d, 2, ctx->d_idx[d], ctx->d_pos[d], ctx->Nd[d], 0);
+                    rc = launch_score_d(ctx, d, 2, ctx->d_idx[d] + ctx->lo[d] * d, ctx->d_pos[d] + ctx->lo[d], ctx->Nd[d], 0);
             ctx->params.nn_engine = keep;
             if (rc) return rc;
         }

@@ -115,4 +115,21 @@ __global__ void __launch_bounds__(256) k_cover_rows(const uint8_t* idx, const i6
     }
 }
 
+// positions are ascending inside a size class: [lo, hi) of the rows whose position lies in [b, e)
+__global__ void k_pos_bounds(const i64* pos, i64 n, i64 b, i64 e, i64* out2)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    i64 lo = 0, hi = n;
+    while (lo < hi) { const i64 m = (lo + hi) >> 1; if (pos[m] < b) lo = m + 1; else hi = m; }
+    out2[0] = lo;
+    hi = n;
+    while (lo < hi) { const i64 m = (lo + hi) >> 1; if (pos[m] < e) lo = m + 1; else hi = m; }
+    out2[1] = lo;
+}
+
+__global__ void __launch_bounds__(256) k_pos_shift(i64* pos, i64 n, i64 delta)
+{
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) pos[i] -= delta;
+}
+
 }  // namespace sdpcs

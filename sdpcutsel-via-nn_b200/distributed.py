@@ -14,6 +14,14 @@ def shard_range(N, world, rank):
     return rank * N // world, (rank + 1) * N // world
 
 
+def shard_cover(engine, world, rank):
+    """Restrict the cover `engine` holds (all-subsets, or a pattern-E / list cover set in full on every rank) to this rank's
+    contiguous range of candidates (sdpcs_cover_restrict); returns (begin, end)."""
+    b, e = shard_range(engine.num_candidates, world, rank)
+    engine.cover_restrict(b, e)
+    return b, e
+
+
 class ShardedSelector(object):
     """engine: an _capi.Engine (or any object with score/topk/counts/merge_topk) whose cover is this rank's shard."""
 

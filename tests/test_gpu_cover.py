@@ -139,3 +139,57 @@ def test_errors(capi):
     eng.set_cover_all(3)
     with pytest.raises(capi.SdpcsError):
         eng.cover_rows()                                              # no list cover
+
+
+@pytest.mark.parametrize("dim", [3, 5])
+def test_cover_restrict_shards_a_list_cover(capi, blobs, golden, dim):
+    """sdpcs_cover_restrict: every rank builds the pattern cover and keeps its contiguous shard.  Scores of
+    a shard are the slice of the full scores, agg_idx values are unchanged, and the merge of the shard selections is
+    the full selection."""
+    n, Q_arr, adj = inst_arrays(golden, "spar040-030-1")
+    vv = golden["mix_vars"]
+
+    def engine():
+        eng = capi.Engine(0)
+        for d in range(2, dim + 1):
+            eng.set_weights(d, blobs[d])
+        eng.set_instance(n, Q_arr)
+        return eng
+
+    full = engine()
+    N = full.set_cover_pattern(dim, adj)
+    rows = full.cover_rows()
+    full.score(vv, 3)
+    lam, obj = full.scores()
+    k = max(1, N // 10)
+    want = full.select(2, vv, k)
+    cuts = [0, N // 3 + 1, N // 3 + 1, 2 * N // 3, N]          # includes an empty shard
+    parts = []
+    for b, e in zip(cuts[:-1], cuts[1:]):
+        eng = engine()
+        eng.set_cover_pattern(dim, adj)
+        eng.cover_restrict(b, e)
+        assert eng.num_candidates == e - b
+        assert np.array_equal(eng.cover_rows(), rows[b:e])
+        if e > b:
+            eng.score(vv, 3)
+            l2, o2 = eng.scores()
+            assert np.array_equal(l2, lam[b:e]) and np.array_equal(o2, obj[b:e])
+            parts.append(eng.topk(2, k))
+            with pytest.raises(capi.SdpcsError):
+                eng.cover_restrict(0, 1)                              # a list cover is restricted once
+    gidx = np.concatenate([p[0] for p in parts])
+    gsc = np.concatenate([p[1] for p in parts])
+    perm = full.merge_topk(gsc, None, gidx, k)
+    assert np.array_equal(gidx[perm], want["idx"]) and np.array_equal(gsc[perm], want["score"])
+    with pytest.raises(capi.SdpcsError):
+        full.cover_restrict(5, N + 1)
+    # all-subsets cover: the rank range moves
+    allc = engine()
+    allc.set_cover_all(dim)
+    allc.score(vv, 2)
+    o_all = allc.scores(lam=False)[1]
+    allc.cover_restrict(100, 1000)
+    allc.cover_restrict(50, 500)                                      # relative to the current range: ranks 150 .. 600
+    allc.score(vv, 2)
+    assert np.array_equal(allc.scores(lam=False)[1], o_all[150:600])
