@@ -31,6 +31,8 @@ WORKLOADS = {
     "cfg4": dict(n=125, rho=5, density=0.75, k=5000, name="synthetic n=125 d=75% BoxQP, rho=5, all C(125,5)=234,531,275 subsets, eig+NN_5D, strat 4, k=5000"),
     "cfg3": dict(n=125, rho=4, density=0.75, k=5000, name="synthetic n=125 d=75% BoxQP, rho=4, all C(125,4)=9,691,375 subsets, eig+NN_4D, strat 4, k=5000"),
     "small": dict(n=60, rho=5, density=0.75, k=5000, name="synthetic n=60 rho=5 (debug)"),
+    "patternE5": dict(n=125, rho=5, density=0.75, k=5000, pattern=True,
+                      name="synthetic n=125 d=75% BoxQP, rho=5, pattern-E cover P^E_5 (12.6 M cliques, built on the device), eig+NN, strat 4, k=5000"),
 }
 
 
@@ -162,7 +164,7 @@ def main():
     N = comb(n, rho)
     r0, r1 = shard_range(N, world, rank)
 
-    Q_arr, _ = pkg.synthetic.boxqp_arrays(pkg.synthetic.instance(n, wl["density"], seed=7))
+    Q_arr, adj = pkg.synthetic.boxqp_arrays(pkg.synthetic.instance(n, wl["density"], seed=7))
     vv = pkg.synthetic.lp_point(n, seed=8)
     stream = torch.cuda.Stream(device=dev)
     with torch.cuda.stream(stream):
@@ -171,7 +173,13 @@ def main():
         eng.set_params(nn_engine=pkg._capi.NN_DMMA if args.nn_engine == "dmma" else pkg._capi.NN_TCGEN05, nn_fused_prep=int(args.fused_prep))
         eng.set_weights(rho, pkg.nn_weights.load_packed(rho))
         eng.set_instance(n, Q_arr)
-        eng.set_cover_all(rho, r0, r1)
+        if wl.get("pattern"):
+            for d in range(2, rho):
+                eng.set_weights(d, pkg.nn_weights.load_packed(d))
+            N = eng.set_cover_pattern(rho, adj)                      # every rank builds the cover, then keeps its shard
+            r0, r1 = pkg.distributed.shard_cover(eng, world, rank)
+        else:
+            eng.set_cover_all(rho, r0, r1)
         sel = ShardedSelector(eng, device=dev if world > 1 else None)
         peak = eng.fp64_peak()
 
