@@ -655,7 +655,7 @@ static int upload_vars(sdpcs_ctx* ctx, const double* vars_values)
 
 constexpr int NN_WARPS = 16;
 
-constexpr i64 I8_CHUNK_TILES = 65536;   // 8.4 M candidates, 1.3 GB of digit images per chunk
+constexpr i64 I8_CHUNK_TILES = 262144;  // 33.6 M candidates, 5.2 GB of digit images per chunk (7 chunks at cfg4 size)
 
 static int ensure_tiles(sdpcs_ctx* ctx, i64 n_tiles)
 {
