@@ -44,12 +44,14 @@ lines = ["ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_
          "%-28s %6s %12s %7s %12s %12s" % ("kernel", "count", "total ms", "share", "DRAM rd GB", "DRAM wr GB")]
 for k, a in agg.items():
     lines.append("%-28s %6d %12.3f %6.1f%% %12.3f %12.3f" % (k[:28], a[0], a[1], 100 * a[1] / tot, a[2] / 1e9, a[3] / 1e9))
-nsteps = agg["k_mlp_i8<4, 0>" if "k_mlp_i8<4, 0>" in agg else [k for k in agg if k.startswith("k_mlp_i8")][0]][0] / 28.0
 mk = [k for k in agg if k.startswith("k_mlp_i8")][0]
 pk = [k for k in agg if k.startswith("k_prep_i8")][0]
 fk = [k for k in agg if k.startswith("k_score_feas")][0]
-per_step = {k: (agg[k][1] / (agg[k][0] / (28.0 if k != fk else 1.0)), (agg[k][2] + agg[k][3]) / (agg[k][0] / (28.0 if k != fk else 1.0))) for k in (mk, pk, fk)}
-lines += ["", "per scoring pass over 234,531,275 candidates (28 chunks): "
+dmma_passes = sum(a[0] for k, a in agg.items() if k.startswith("k_score_nn"))
+passes = max(agg[fk][0] - dmma_passes, 1)             # scoring passes of the tcgen05 engine among the captured launches
+chunks = agg[mk][0] / float(passes)
+per_step = {k: (agg[k][1] / (agg[k][0] / (chunks if k != fk else 1.0)), (agg[k][2] + agg[k][3]) / (agg[k][0] / (chunks if k != fk else 1.0))) for k in (mk, pk, fk)}
+lines += ["", "per scoring pass over 234,531,275 candidates (%g chunks): " % chunks
           + "; ".join("%s %.1f ms, %.2f GB DRAM" % (k, v[0], v[1] / 1e9) for k, v in per_step.items())]
 open(os.path.join(P, "ncu_launches_cfg4_%s_summary.txt" % ver), "w").write("\n".join(lines) + "\n")
 print("\n".join(lines))
