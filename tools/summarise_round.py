@@ -71,7 +71,7 @@ keys = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
         "lts__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
 out = ["ncu --set full --clock-control none --import-source on -k 'regex:k_score_feas|k_prep_i8|k_mlp_i8' -c 3 python bench.py --steps 1 --warmup 1 --no-cpu-baseline",
-       "(cfg4; k_score_feas: whole shard of 234,531,275 candidates; k_prep_i8 / k_mlp_i8: first chunk of 65,536 tiles = 8,388,608 candidates)"]
+       "(cfg4; k_score_feas: whole shard of 234,531,275 candidates; k_prep_i8 / k_mlp_i8: first staging chunk (262,144 tiles = 33,554,432 candidates since v7; 65,536 tiles before))"]
 dram = {}
 for r in rr[2:]:
     name = r[h.index("Kernel Name")]
