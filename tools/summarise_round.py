@@ -103,8 +103,8 @@ step_bytes = sum(v[1] for v in per_step.values())
 json.dump({"source": "profiles/r01/ncu_launches_cfg4_%s_summary.txt" % ver,
            "kernels": {k: {"ms_per_pass": v[0], "dram_bytes_per_pass": v[1]} for k, v in per_step.items()},
            "score_kernel_dram_bytes_per_launch": step_bytes,
-           "note": "one scoring pass over 234,531,275 candidates = 1 x k_score_feas + 28 x (k_prep_i8 + k_mlp_i8): dram__bytes_read.sum + "
+           "note": "one scoring pass over 234,531,275 candidates = 1 x k_score_feas + %g x (k_prep_i8 + k_mlp_i8): dram__bytes_read.sum + " % chunks +
                    "dram__bytes_write.sum summed over those launches; algorithmic bytes = 16 B x candidates = 3.75e9 (lam + obj); the rest is the "
-                   "layer-0 digit image staged through HBM (240 B per candidate, written by k_prep_i8 and read back by TMA)"},
+                   "layer-0 digit image staged through HBM (156 B per candidate, written by k_prep_i8 and read back by TMA)"},
           open(os.path.join(ROOT, "profiles", "ncu_summary.json"), "w"), indent=1)
 print("step DRAM bytes", step_bytes)
