@@ -49,6 +49,17 @@ typedef struct sdpcs_params {
     int32_t nn_engine;       /* NN_rhoD evaluation: SDPCS_NN_TCGEN05 (default) or SDPCS_NN_DMMA */
     int32_t nn_fused_prep;   /* tcgen05 engine: 0 = layer-0 digit images staged through HBM by a separate kernel (default),
                               * 1 = built in shared memory by producer warps of the MLP kernel (no image in HBM) */
+    /* Near-tie guard (SURVEY 7 hard part 1).  The reference's order among candidates whose scores agree to rounding
+     * noise is decided by LAPACK dsyevd / libm exp round-off (cut_select_qp.py:647-654, 599-601); device scores differ
+     * from those by <= ~1e-14 (lam) / ~1e-10 (obj).  With a guard > 0 a selection also returns every candidate ranked
+     * after the k-th whose score is within the guard of the k-th score (sdpcs_last_band), classifies with thresholds
+     * relaxed by the guard in modes 1 and 3 (no candidate the reference could count as violated / positive is dropped on
+     * the device), and counts the candidates whose classification lies inside the guard.  The caller re-scores near-tie
+     * runs with the reference's own arithmetic (the Python mirror does: numpy eigvalsh / exact NN) and re-sorts them.
+     * 0 disables the relaxation; the band then holds the exact ties of the k-th score only. */
+    double guard_lam;        /* absolute guard on lam_min scores, default 1e-12 */
+    double guard_obj;        /* absolute guard on optimality measures, default 1e-9 (mirror: 4e-12 * rho * max|Q_arr|) */
+    int64_t band_cap;        /* room for near ties after the k winners, default 65536 entries */
 } sdpcs_params;
 
 /* NN engines.  Both evaluate neural_net_{2..5}D (cut_select_qp.py:579-582) to FP64 accuracy:
@@ -146,6 +157,18 @@ int sdpcs_max_pos_nonviolated(sdpcs_ctx *ctx, double *out);
  * Outputs (length k, first *out_n valid, already in final order): agg_idx, key score, lam, obj. */
 int sdpcs_topk(sdpcs_ctx *ctx, int mode, int64_t k, double pivot_obj, int64_t pivot_idx, int all_walked,
                int64_t *out_idx, double *out_score, double *out_lam, double *out_obj, int64_t *out_n);
+
+/* Guard band of the last sdpcs_topk / sdpcs_select pass (see sdpcs_params.guard_*): the candidates ranked right after the
+ * winners whose primary score (-lam in mode 1, obj in modes 2 and 3, the re-scored measure in mode 4; for sdpcs_select
+ * strat 4 on the strong-prefix path: obj) is within the guard of the k-th score, in selection order; first min(cap, n)
+ * are written, *out_n = how many.  out_info[4] (may be NULL) = {n_band, band_open, n_unc_lam, n_unc_obj}:
+ * n_band near ties after the winners; band_open = 1 if more near ties exist than could be collected (a tie class larger
+ * than band_cap); n_unc_lam / n_unc_obj = candidates of the whole cover with |lam - thres_neg_eigval| <= guard_lam /
+ * |obj - thres_min_opt| <= guard_obj, i.e. whose violated / positive classification round-off could flip.
+ * A selection is free of near-tie ambiguity iff n_band = 0, no two consecutive winners are closer than the guard and,
+ * where the strategy classifies, n_unc_* = 0. */
+int sdpcs_last_band(sdpcs_ctx *ctx, int64_t cap, int64_t *out_idx, double *out_score, double *out_lam,
+                    double *out_obj, int64_t *out_n, int64_t *out_info);
 
 /* Merge m entries gathered from several shards into the global top-k with the same comparator
  * (score desc, obj2 desc, agg_idx asc); perm receives the positions of the winners, in order. */

@@ -21,6 +21,7 @@ EXPORTS = [
     "sdpcs_select", "sdpcs_unrank", "sdpcs_binom", "sdpcs_gen_cuts", "sdpcs_eigendecomp", "sdpcs_set_tri_pattern",
     "sdpcs_triangles", "sdpcs_nn_eval", "sdpcs_nn_debug_layer", "sdpcs_fp64_peak",
     "sdpcs_set_cover_pattern", "sdpcs_get_cover_rows", "sdpcs_cover_restrict", "sdpcs_gen_cuts_csr", "sdpcs_triangle_rows_csr", "sdpcs_dense_eigcuts", "sdpcs_max_pos_nonviolated",
+    "sdpcs_last_band",
 ]
 
 NN_TCGEN05, NN_DMMA = 0, 1
@@ -29,7 +30,7 @@ NN_TCGEN05, NN_DMMA = 0, 1
 class Params(ctypes.Structure):
     _fields_ = [("thres_min_opt", c_dbl), ("thres_neg_eigval", c_dbl), ("big_m", c_dbl), ("thres_tri_viol", c_dbl),
                 ("thres_tri_dense", ctypes.c_int32), ("jacobi_sweeps", ctypes.c_int32), ("nn_engine", ctypes.c_int32),
-                ("nn_fused_prep", ctypes.c_int32)]
+                ("nn_fused_prep", ctypes.c_int32), ("guard_lam", c_dbl), ("guard_obj", c_dbl), ("band_cap", c_i64)]
 
 
 class Timings(ctypes.Structure):
@@ -82,6 +83,7 @@ class Engine(object):
             msg = self._lib.sdpcs_last_error(None)
             self._ctx = None
             raise SdpcsError("sdpcs_create failed (%d): %s" % (rc, msg.decode() if msg else ""))
+        self._params = None
         self.n = 0
         self.big_m = 1000.0            # sdpcs_default_params
         self.rho = 0
@@ -108,12 +110,23 @@ class Engine(object):
         self._ck(self._lib.sdpcs_set_stream(self._ctx, c_vp(stream_ptr)))
 
     def set_params(self, **kw):
-        p = Params()
-        self._lib.sdpcs_default_params(ctypes.byref(p))
+        """Update algorithmic / engine parameters (sdpcs_params); fields not named keep their current value."""
+        if self._params is None:
+            self._params = Params()
+            self._lib.sdpcs_default_params(ctypes.byref(self._params))
+        p = self._params
         for k, v in kw.items():
+            if not hasattr(p, k):
+                raise AttributeError("sdpcs_params has no field %r" % k)
             setattr(p, k, v)
         self._ck(self._lib.sdpcs_set_params(self._ctx, ctypes.byref(p)))
         self.big_m = float(p.big_m)
+
+    @property
+    def params(self):
+        if self._params is None:
+            self.set_params()
+        return self._params
 
     def set_weights(self, rho, blob):
         blob = _f64(blob)
@@ -162,8 +175,10 @@ class Engine(object):
         return N.value
 
     # -- scoring / selection -----------------------------------------------------------------------
-    def _vars(self, vars_values):
+    def _vars(self, vars_values, required=False):
         if vars_values is None:          # re-use the LP point resident on the device
+            if required:
+                raise ValueError("vars_values is required here")
             return None
         v = _f64(vars_values)
         if v.size != self.n * (self.n + 1) // 2 + self.n:
@@ -195,6 +210,21 @@ class Engine(object):
                                       _ptr(idx), _ptr(sc), _ptr(lam), _ptr(obj), ctypes.byref(n)))
         m = n.value
         return idx[:m], sc[:m], lam[:m], obj[:m]
+
+    def last_band(self, cap=None):
+        """Guard band of the last topk / select pass (sdpcs_last_band): the near ties of the k-th score that follow the
+        winners, in selection order, plus the guard counters."""
+        info = np.zeros(4, dtype=np.int64)
+        n = c_i64()
+        self._ck(self._lib.sdpcs_last_band(self._ctx, c_i64(0), None, None, None, None, ctypes.byref(n), _ptr(info)))
+        m = int(info[0]) if cap is None else min(int(info[0]), int(cap))
+        kk = max(m, 1)
+        idx, sc, lam, obj = np.empty(kk, np.int64), np.empty(kk), np.empty(kk), np.empty(kk)
+        if m > 0:
+            self._ck(self._lib.sdpcs_last_band(self._ctx, c_i64(m), _ptr(idx), _ptr(sc), _ptr(lam), _ptr(obj), ctypes.byref(n), _ptr(info)))
+            m = n.value
+        return dict(idx=idx[:m], score=sc[:m], lam=lam[:m], obj=obj[:m], n_band=int(info[0]), band_open=int(info[1]),
+                    n_unc_lam=int(info[2]), n_unc_obj=int(info[3]))
 
     def max_pos_nonviolated(self):
         out = c_dbl()
@@ -236,7 +266,7 @@ class Engine(object):
         width = rho + rho * (rho + 1) // 2
         ind, val = np.empty((m, width), np.int64), np.empty((m, width))
         rhs, lam, viol = np.empty(m), np.empty(m), np.empty(m, np.uint8)
-        v = _f64(vars_values)
+        v = self._vars(vars_values, required=True)
         self._ck(self._lib.sdpcs_gen_cuts(self._ctx, c_int(rho), _ptr(sets), c_i64(m), _ptr(v), _ptr(ind), _ptr(val), _ptr(rhs),
                                           _ptr(lam), _ptr(viol)))
         return ind, val, rhs, lam, viol.astype(bool)
@@ -248,7 +278,7 @@ class Engine(object):
         width = rho + rho * (rho + 1) // 2
         rowptr, ind, val = np.zeros(m + 1, np.int64), np.empty(m * width, np.int64), np.empty(m * width)
         rhs, src, nrows = np.empty(m), np.empty(m, np.int64), c_i64()
-        v = _f64(vars_values)
+        v = self._vars(vars_values, required=True)
         self._ck(self._lib.sdpcs_gen_cuts_csr(self._ctx, c_int(rho), _ptr(sets), c_i64(m), _ptr(v), _ptr(rowptr), _ptr(ind), _ptr(val),
                                               _ptr(rhs), _ptr(src), ctypes.byref(nrows)))
         r = nrows.value
@@ -257,7 +287,7 @@ class Engine(object):
 
     def dense_eigcuts(self, vars_values):
         """Strat 0 (cut_select_qp.py:757-786): dict(eigvals (n+1,), ind (width,), val (ncuts, width), rhs (ncuts,))."""
-        v = _f64(vars_values)
+        v = self._vars(vars_values, required=True)
         n = self.n
         nb_lifted = n * (n + 1) // 2
         width = n + nb_lifted
@@ -278,7 +308,7 @@ class Engine(object):
         self._ck(self._lib.sdpcs_set_tri_pattern(self._ctx, _ptr(a)))
 
     def triangles(self, vars_values, kmax):
-        v = _f64(vars_values)
+        v = self._vars(vars_values, required=True)
         kk = max(int(kmax), 1)
         rank, typ, viol, dens = np.empty(kk, np.int64), np.empty(kk, np.int8), np.empty(kk), np.empty(kk, np.int8)
         n, nv, nt = c_i64(), c_i64(), c_i64()

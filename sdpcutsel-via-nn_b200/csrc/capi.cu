@@ -51,17 +51,21 @@ struct sdpcs_ctx {
     double *d_lam = nullptr, *d_obj = nullptr;
     i64 score_cap = 0;
     int have = 0;
-    // selection scratch
-    u64 *d_key1 = nullptr, *d_key2 = nullptr;
-    i64 key_cap = 0, key2_cap = 0;
+    // selection scratch (keys are recomputed from lam / obj in every pass; d_key1 holds the triangle keys only)
+    u64* d_key1 = nullptr;
+    i64 key_cap = 0;
     SelState* d_state = nullptr;
+    SelState* h_state = nullptr;   // pinned copy of the state after a selection
     u64 *d_c_k1 = nullptr, *d_c_k2 = nullptr, *d_s_k1 = nullptr, *d_s_k2 = nullptr;
     i64 *d_c_idx = nullptr, *d_s_idx = nullptr, *d_s_perm = nullptr;
     double *d_o_score = nullptr, *d_o_lam = nullptr, *d_o_obj = nullptr;
-    i64 out_cap = 0;
-    void* h_out = nullptr;         // pinned download staging
-    size_t h_out_bytes = 0;
+    i64 out_cap = 0, sel_cap = 0;  // allocated entries / entries the last selection could collect (k + band_cap)
+    void* h_out = nullptr;         // pinned download staging: [idx | score | lam | obj], h_out_stride bytes each
+    size_t h_out_bytes = 0, h_out_stride = 0;
+    i64 h_out_rows = 0, h_out_k = 0;   // rows downloaded by the last selection (winners + guard band), winners among them
+    int last_mode = 0;
     i64 last_counts[3] = {0, 0, 0};
+    i64 last_guard[4] = {0, 0, 0, 0};  // band entries, band open, n_unc_lam, n_unc_obj of the last selection
     double last_max_pos_nonviol = -INFINITY;   // largest obj among (obj > thres_min_opt and not violated), last top-k pass
     // triangles
     uint8_t* d_adj = nullptr;
@@ -241,6 +245,9 @@ extern "C" int sdpcs_default_params(sdpcs_params* p)
     p->jacobi_sweeps = 0;
     p->nn_engine = SDPCS_NN_TCGEN05;
     p->nn_fused_prep = 0;
+    p->guard_lam = 1e-12;
+    p->guard_obj = 1e-9;
+    p->band_cap = 65536;
     return SDPCS_OK;
 }
 
@@ -270,7 +277,7 @@ extern "C" int sdpcs_create(sdpcs_ctx** out, int device)
     sdpcs_default_params(&ctx->params);
     memset(&ctx->tm, 0, sizeof(ctx->tm));
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc(&ctx->d_state, sizeof(SelState)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_state, sizeof(SelState)) != cudaSuccess || cudaMallocHost(&ctx->h_state, sizeof(SelState)) != cudaSuccess ||
         cudaMalloc(&ctx->d_tri_counters, 2 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMalloc(&ctx->d_status, sizeof(int)) != cudaSuccess || cudaMallocHost(&ctx->h_status, sizeof(int)) != cudaSuccess ||
         cudaMemset(ctx->d_status, 0, sizeof(int)) != cudaSuccess) {
@@ -289,7 +296,7 @@ extern "C" int sdpcs_destroy(sdpcs_ctx* ctx)
     if (!ctx) return SDPCS_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    void* ptrs[] = {ctx->d_Q, ctx->d_vars, ctx->d_lam, ctx->d_obj, ctx->d_key1, ctx->d_key2, ctx->d_state, ctx->d_c_k1,
+    void* ptrs[] = {ctx->d_Q, ctx->d_vars, ctx->d_lam, ctx->d_obj, ctx->d_key1, ctx->d_state, ctx->d_c_k1,
                     ctx->d_c_k2, ctx->d_s_k1, ctx->d_s_k2, ctx->d_c_idx, ctx->d_s_idx, ctx->d_s_perm, ctx->d_o_score,
                     ctx->d_o_lam, ctx->d_o_obj, ctx->d_adj, ctx->d_tri_counters, ctx->d_scratch, ctx->d_tiles, ctx->d_status};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -302,6 +309,7 @@ extern "C" int sdpcs_destroy(sdpcs_ctx* ctx)
     if (ctx->h_vars) cudaFreeHost(ctx->h_vars);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
+    if (ctx->h_state) cudaFreeHost(ctx->h_state);
     for (auto& ev : ctx->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -861,32 +869,84 @@ static int ensure_out(sdpcs_ctx* ctx, i64 k)
     return SDPCS_OK;
 }
 
-// radix-select + collect + sort over (key1, key2, idx); results in d_s_k1/d_s_k2/d_s_idx, count in state
-static int run_select(sdpcs_ctx* ctx, const u64* key1, const u64* key2, const i64* idx, i64 N, i64 base, i64 k)
+// output capacity for a selection of k: the winners plus room for their near ties (params.band_cap)
+static i64 sel_capacity(const sdpcs_ctx* ctx, i64 k) { return std::max<i64>(k, 1) + std::max<i64>(ctx->params.band_cap, 0); }
+// the radix select stops as soon as this many keys or fewer remain at or above the prefix
+static i64 sel_cap_exit(const sdpcs_ctx* ctx, i64 k) { return std::min<i64>(sel_capacity(ctx, k), k + std::max<i64>(k, 4096)); }
+
+static double guard_delta(const sdpcs_ctx* ctx, int mode)
 {
-    SelArgs sa{key1, key2, idx, N, base, ctx->d_state};
-    const int threads = 512;
-    const unsigned grid = (unsigned)std::max<i64>(1, std::min<i64>((N + threads - 1) / threads, (i64)ctx->sms * 4));
+    if (mode == 0) return -1.0;
+    const double d = (mode == 1) ? ctx->params.guard_lam : ctx->params.guard_obj;
+    return d > 0.0 ? d : 0.0;           // 0: exact ties of the k-th score only
+}
+
+template <int MODE>
+static void launch_hist_scan(sdpcs_ctx* ctx, const KeySrc& ks, unsigned grid, int level, int shift, int width, bool first,
+                             bool last, int next_level, i64 k, i64 cap_exit)
+{
+    if (first) k_sel_hist<MODE, true><<<grid, 512, 0, ctx->stream>>>(ks, level, shift, width);
+    else k_sel_hist<MODE, false><<<grid, 512, 0, ctx->stream>>>(ks, level, shift, width);
+    k_sel_scan<<<1, 1024, 0, ctx->stream>>>(ctx->d_state, level, shift, width, first ? 1 : 0, last ? 1 : 0, next_level, k, cap_exit);
+    ctx->tm.select_launches += 2;
+}
+
+template <int MODE>
+static void launch_collect_sort(sdpcs_ctx* ctx, const KeySrc& ks, i64 cap, i64 cap_exit, double delta)
+{
+    const unsigned cgrid = (unsigned)std::max<i64>(1, std::min<i64>((ks.N + 511) / 512, (i64)ctx->sms * 8));
+    k_sel_collect<MODE><<<cgrid, 256, 0, ctx->stream>>>(ks, cap, ctx->d_c_k1, ctx->d_c_k2, ctx->d_c_idx);
+    k_rank_sort<<<(unsigned)((cap_exit + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_state, 0, cap, ctx->d_c_k1, ctx->d_c_k2,
+                                                                                ctx->d_c_idx, ctx->d_s_k1, ctx->d_s_k2, ctx->d_s_idx);
+    k_sel_finish<<<1, 32, 0, ctx->stream>>>(ctx->d_state, ctx->d_s_k1, cap, delta);
+    ctx->tm.select_launches += 3;
+}
+
+// Radix select + collect + sort over the 3-level key of `ks`; results in d_s_k1/d_s_k2/d_s_idx, counts in the state
+// (copied to ctx->h_state).  Fast path: three level-0 passes, then collect (the scan kernels stop the select as soon as
+// the keys above the prefix fit); the remaining passes only run when a tie class is larger than the buffers.
+template <int MODE>
+static int run_select_t(sdpcs_ctx* ctx, KeySrc ks, i64 k)
+{
+    ks.st = ctx->d_state;
+    const i64 cap = sel_capacity(ctx, k), cap_exit = sel_cap_exit(ctx, k);
+    ctx->sel_cap = cap;
+    const double delta = guard_delta(ctx, MODE);
+    const unsigned grid = (unsigned)std::max<i64>(1, std::min<i64>((ks.N + 1023) / 1024, (i64)ctx->sms * 4));
     static const int shifts0[6] = {53, 42, 31, 20, 10, 0}, widths0[6] = {11, 11, 11, 11, 10, 10};
-    for (int p = 0; p < 6; ++p) {
-        k_sel_hist<<<grid, threads, 0, ctx->stream>>>(sa, 0, shifts0[p], widths0[p], p == 0);
-        k_sel_scan<<<1, 1024, 0, ctx->stream>>>(ctx->d_state, 0, shifts0[p], widths0[p], p == 0, p == 5, key2 ? 1 : 2, k);
+    const int next0 = (MODE == 4) ? 1 : 2;
+    for (int p = 0; p < 3; ++p) launch_hist_scan<MODE>(ctx, ks, grid, 0, shifts0[p], widths0[p], p == 0, false, next0, k, cap_exit);
+    launch_collect_sort<MODE>(ctx, ks, cap, cap_exit, delta);
+    CU(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(SelState), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->h_state->done) {
+        for (int p = 3; p < 6; ++p) launch_hist_scan<MODE>(ctx, ks, grid, 0, shifts0[p], widths0[p], false, p == 5, next0, k, cap_exit);
+        if (MODE == 4)
+            for (int p = 0; p < 6; ++p) launch_hist_scan<MODE>(ctx, ks, grid, 1, shifts0[p], widths0[p], false, p == 5, 2, k, cap_exit);
+        for (int p = 0; p < 4; ++p) launch_hist_scan<MODE>(ctx, ks, grid, 2, 33 - 11 * p, 11, false, p == 3, -1, k, cap_exit);
+        launch_collect_sort<MODE>(ctx, ks, cap, cap_exit, delta);
+        CU(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(SelState), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
     }
-    if (key2)
-        for (int p = 0; p < 6; ++p) {
-            k_sel_hist<<<grid, threads, 0, ctx->stream>>>(sa, 1, shifts0[p], widths0[p], 0);
-            k_sel_scan<<<1, 1024, 0, ctx->stream>>>(ctx->d_state, 1, shifts0[p], widths0[p], 0, p == 5, 2, k);
+    if (ctx->h_state->done == 2 && ctx->h_state->band_open && delta >= 0.0) {
+        // near ties of the k-th score reach below the collected prefix: collect again from the band key (one more pass);
+        // if that overflows the buffers, fall back to the first collection and leave the band flagged open
+        const SelState first = *ctx->h_state;
+        k_sel_lower<<<1, 32, 0, ctx->stream>>>(ctx->d_state);
+        launch_collect_sort<MODE>(ctx, ks, cap, cap, delta);
+        CU(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(SelState), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if ((i64)ctx->h_state->out_count > cap) {
+            SelState redo = first;
+            redo.out_count = 0;
+            CU(cudaMemcpyAsync(ctx->d_state, &redo, sizeof(SelState), cudaMemcpyHostToDevice, ctx->stream));
+            launch_collect_sort<MODE>(ctx, ks, cap, cap_exit, delta);
+            CU(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(SelState), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            ctx->h_state->band_open = 1;
         }
-    for (int p = 0; p < 4; ++p) {
-        k_sel_hist<<<grid, threads, 0, ctx->stream>>>(sa, 2, 33 - 11 * p, 11, 0);
-        k_sel_scan<<<1, 1024, 0, ctx->stream>>>(ctx->d_state, 2, 33 - 11 * p, 11, 0, p == 3, -1, k);
     }
-    const unsigned cgrid = (unsigned)std::max<i64>(1, std::min<i64>((N + 255) / 256, (i64)ctx->sms * 8));
-    k_sel_collect<<<cgrid, 256, 0, ctx->stream>>>(sa, ctx->out_cap, ctx->d_c_k1, ctx->d_c_k2, ctx->d_c_idx);
-    k_rank_sort<<<(unsigned)((k + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_state, 0, ctx->d_c_k1, ctx->d_c_k2, ctx->d_c_idx,
-                                                                        ctx->d_s_k1, ctx->d_s_k2, ctx->d_s_idx);
     CU(cudaGetLastError());
-    ctx->tm.select_launches += 2 * (6 + (key2 ? 6 : 0) + 4) + 2;
     return SDPCS_OK;
 }
 
@@ -897,61 +957,68 @@ static int topk_device(sdpcs_ctx* ctx, int mode, i64 k, double pivot_obj, i64 pi
     if ((ctx->have & need) != need) return ctx->fail(SDPCS_ERR_STATE, "scores needed by this mode are not resident; call sdpcs_score");
     if (k < 0) return ctx->fail(SDPCS_ERR_INVALID, "k < 0");
     k = std::min<i64>(k, ctx->N);
-    int rc = ensure_dev(ctx, ctx->d_key1, ctx->key_cap, ctx->N);
+    int rc = ensure_out(ctx, sel_capacity(ctx, k));
     if (rc) return rc;
-    if (mode == 4 && (rc = ensure_dev(ctx, ctx->d_key2, ctx->key2_cap, ctx->N))) return rc;
-    if ((rc = ensure_out(ctx, std::max<i64>(k, 1)))) return rc;
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
     ctx->tm.select_launches = 0;
     k_sel_reset<<<1, 256, 0, ctx->stream>>>(ctx->d_state);
-    KeyArgs ka;
-    ka.lam = (ctx->have & 1) ? ctx->d_lam : nullptr;
-    ka.obj = (ctx->have & 2) ? ctx->d_obj : nullptr;
-    ka.N = ctx->N; ka.base = ctx->base; ka.mode = mode;
-    ka.thr_eig = ctx->params.thres_neg_eigval; ka.thr_opt = ctx->params.thres_min_opt; ka.big_m = ctx->params.big_m;
-    ka.pivot_obj = pivot_obj; ka.pivot_idx = pivot_idx; ka.all_walked = all_walked;
-    ka.key1 = ctx->d_key1; ka.key2 = (mode == 4) ? ctx->d_key2 : nullptr; ka.st = ctx->d_state;
-    const unsigned grid = (unsigned)std::max<i64>(1, std::min<i64>((ctx->N + 255) / 256, (i64)ctx->sms * 8));
-    k_make_keys<<<grid, 256, 0, ctx->stream>>>(ka);
-    ctx->tm.select_launches += 2;
-    if (k > 0) {
-        rc = run_select(ctx, ctx->d_key1, ka.key2, nullptr, ctx->N, ctx->base, k);
-        if (rc) return rc;
-        k_sel_gather<<<(unsigned)std::max<i64>(1, (k + 255) / 256), 256, 0, ctx->stream>>>(
-            ctx->d_state, ctx->d_s_k1, ctx->d_s_idx, ctx->base, ka.lam, ka.obj, ctx->d_o_score, ctx->d_o_lam, ctx->d_o_obj);
+    ctx->tm.select_launches++;
+    KeySrc ks;
+    memset(&ks, 0, sizeof(ks));
+    ks.lam = (ctx->have & 1) ? ctx->d_lam : nullptr;
+    ks.obj = (ctx->have & 2) ? ctx->d_obj : nullptr;
+    ks.N = ctx->N; ks.base = ctx->base;
+    ks.thr_eig = ctx->params.thres_neg_eigval; ks.thr_opt = ctx->params.thres_min_opt; ks.big_m = ctx->params.big_m;
+    ks.guard_lam = std::max(ctx->params.guard_lam, 0.0); ks.guard_obj = std::max(ctx->params.guard_obj, 0.0);
+    ks.pivot_obj = pivot_obj; ks.pivot_idx = pivot_idx; ks.all_walked = all_walked;
+    // k == 0 still runs the first pass: it fills the counters (n_violated, n_strong, ...)
+    switch (mode) {
+    case 1: rc = run_select_t<1>(ctx, ks, k); break;
+    case 2: rc = run_select_t<2>(ctx, ks, k); break;
+    case 3: rc = run_select_t<3>(ctx, ks, k); break;
+    default: rc = run_select_t<4>(ctx, ks, k); break;
+    }
+    if (rc) return rc;
+    const i64 m = std::min<i64>((i64)ctx->h_state->out_count, ctx->sel_cap);
+    if (m > 0) {
+        k_sel_gather<<<(unsigned)std::max<i64>(1, (m + 255) / 256), 256, 0, ctx->stream>>>(
+            ctx->d_state, ctx->sel_cap, ctx->d_s_k1, ctx->d_s_idx, ctx->base, ks.lam, ks.obj, ctx->d_o_score, ctx->d_o_lam, ctx->d_o_obj);
         ctx->tm.select_launches++;
     }
     CU(cudaEventRecord(ctx->ev[3], ctx->stream));
     ctx->ev_select = true;
+    ctx->last_mode = mode;
     CU(cudaGetLastError());
     return SDPCS_OK;
 }
 
-// download state + the k winners
+// download the winners and their guard band (the state is already on the host)
 static int download_topk(sdpcs_ctx* ctx, i64 k, int64_t* out_idx, double* out_score, double* out_lam, double* out_obj, int64_t* out_n)
 {
-    k = std::min<i64>(k, ctx->N);
-    const size_t kb = (size_t)std::max<i64>(k, 1) * 8;
-    int rc = ensure_hout(ctx, sizeof(SelState) + 4 * kb);
+    const SelState* st = ctx->h_state;
+    const i64 m = std::min<i64>(st->k_out, std::min<i64>(k, ctx->N));
+    const i64 band = std::max<i64>(std::min<i64>(st->band_count, ctx->sel_cap - st->k_out), 0);
+    const i64 tot = st->k_out + band;
+    const size_t cb = (size_t)std::max<i64>(tot, 1) * 8;
+    int rc = ensure_hout(ctx, 4 * cb);
     if (rc) return rc;
     char* h = (char*)ctx->h_out;
-    CU(cudaMemcpyAsync(h, ctx->d_state, sizeof(SelState), cudaMemcpyDeviceToHost, ctx->stream));
-    if (k > 0) {
-        CU(cudaMemcpyAsync(h + sizeof(SelState), ctx->d_s_idx, k * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaMemcpyAsync(h + sizeof(SelState) + kb, ctx->d_o_score, k * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaMemcpyAsync(h + sizeof(SelState) + 2 * kb, ctx->d_o_lam, k * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaMemcpyAsync(h + sizeof(SelState) + 3 * kb, ctx->d_o_obj, k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (tot > 0) {
+        CU(cudaMemcpyAsync(h, ctx->d_s_idx, tot * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(h + cb, ctx->d_o_score, tot * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(h + 2 * cb, ctx->d_o_lam, tot * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(h + 3 * cb, ctx->d_o_obj, tot * 8, cudaMemcpyDeviceToHost, ctx->stream));
     }
     CU(cudaStreamSynchronize(ctx->stream));
-    const SelState* st = (const SelState*)h;
-    i64 m = k > 0 ? std::min<i64>((i64)st->out_count, k) : 0;
+    ctx->h_out_rows = tot; ctx->h_out_stride = cb; ctx->h_out_k = st->k_out;
     ctx->last_counts[0] = ctx->N; ctx->last_counts[1] = st->n_violated; ctx->last_counts[2] = st->n_strong;
     ctx->last_max_pos_nonviol = st->max_pos_nonviol ? dec_key(st->max_pos_nonviol) : -INFINITY;
+    ctx->last_guard[0] = band; ctx->last_guard[1] = st->band_open; ctx->last_guard[2] = st->n_unc_lam; ctx->last_guard[3] = st->n_unc_obj;
     if (out_n) *out_n = m;
-    if (out_idx) memcpy(out_idx, h + sizeof(SelState), m * 8);
-    if (out_score) memcpy(out_score, h + sizeof(SelState) + kb, m * 8);
-    if (out_lam) memcpy(out_lam, h + sizeof(SelState) + 2 * kb, m * 8);
-    if (out_obj) memcpy(out_obj, h + sizeof(SelState) + 3 * kb, m * 8);
+    if (out_idx) memcpy(out_idx, h, m * 8);
+    if (out_score) memcpy(out_score, h + cb, m * 8);
+    if (out_lam) memcpy(out_lam, h + 2 * cb, m * 8);
+    if (out_obj) memcpy(out_obj, h + 3 * cb, m * 8);
     return SDPCS_OK;
 }
 
@@ -964,6 +1031,32 @@ extern "C" int sdpcs_topk(sdpcs_ctx* ctx, int mode, int64_t k, double pivot_obj,
     int rc = topk_device(ctx, mode, k, pivot_obj, pivot_idx, all_walked);
     if (rc) return rc;
     return download_topk(ctx, k, out_idx, out_score, out_lam, out_obj, out_n);
+}
+
+// Guard band of the last sdpcs_topk / sdpcs_select pass: the candidates ranked right after the k winners whose primary
+// score lies within the guard (guard_lam for mode 1, guard_obj otherwise) of the k-th score, in selection order.
+extern "C" int sdpcs_last_band(sdpcs_ctx* ctx, int64_t cap, int64_t* out_idx, double* out_score, double* out_lam,
+                               double* out_obj, int64_t* out_n, int64_t* out_info)
+{
+    if (!ctx || cap < 0 || !out_n) return SDPCS_ERR_INVALID;
+    const i64 band = std::max<i64>(ctx->h_out_rows - ctx->h_out_k, 0);
+    const i64 m = std::min<i64>(band, cap);
+    const char* h = (const char*)ctx->h_out;
+    const size_t cb = ctx->h_out_stride, off = (size_t)ctx->h_out_k * 8;
+    *out_n = m;
+    if (m > 0) {
+        if (out_idx) memcpy(out_idx, h + off, m * 8);
+        if (out_score) memcpy(out_score, h + cb + off, m * 8);
+        if (out_lam) memcpy(out_lam, h + 2 * cb + off, m * 8);
+        if (out_obj) memcpy(out_obj, h + 3 * cb + off, m * 8);
+    }
+    if (out_info) {
+        out_info[0] = ctx->last_guard[0];                                   // near ties of the k-th score after the winners
+        out_info[1] = ctx->last_guard[1] || band > m;                       // 1: more near ties exist than were returned
+        out_info[2] = ctx->last_guard[2];                                   // |lam - thres_neg_eigval| <= guard_lam
+        out_info[3] = ctx->last_guard[3];                                   // |obj - thres_min_opt| <= guard_obj
+    }
+    return SDPCS_OK;
 }
 
 extern "C" int sdpcs_counts(sdpcs_ctx* ctx, int64_t* out3)
@@ -1017,12 +1110,13 @@ extern "C" int sdpcs_select(sdpcs_ctx* ctx, int strat, const double* vars_values
         counts[1] = ctx->last_counts[1];
     } else {
         // pass 1: the strong set S (obj > 0 and violated) by (obj desc, idx asc) -> pivot
-        std::vector<int64_t> sidx(std::max<i64>(k, 1));
-        std::vector<double> sobj(std::max<i64>(k, 1));
         int64_t ns = 0;
         if ((rc = topk_device(ctx, 3, k, 0.0, 0, 0))) return rc;
-        if ((rc = download_topk(ctx, k, sidx.data(), nullptr, nullptr, sobj.data(), &ns))) return rc;
+        if ((rc = download_topk(ctx, k, nullptr, nullptr, nullptr, nullptr, &ns))) return rc;
+        const int64_t* sidx = (const int64_t*)ctx->h_out;
+        const double* sobj = (const double*)((const char*)ctx->h_out + 3 * ctx->h_out_stride);
         const i64 n_viol = ctx->last_counts[1], n_strong_total = ctx->last_counts[2];
+        // (with a guard the list holds the relaxed strong set, a superset; the decisions below use the strict counters)
         const bool all_walked = n_strong_total < k || k == 0;
         const double pobj = all_walked ? 0.0 : sobj[k - 1];
         const i64 pidx = all_walked ? 0 : sidx[k - 1];
@@ -1030,16 +1124,17 @@ extern "C" int sdpcs_select(sdpcs_ctx* ctx, int strat, const double* vars_values
         cudaEventElapsedTime(&ms1, ctx->ev[2], ctx->ev[3]);
         if (combined_is_strong_prefix(ctx->params.big_m, all_walked, k, pobj, ctx->last_max_pos_nonviol)) {
             // the k strong elements up to the pivot get +big_m and nothing else can reach them: the final list IS the
-            // strong list of pass 1 in its own order (ties after the addition fall back to obj desc, idx asc)
+            // strong list of pass 1 in its own order (ties after the addition fall back to obj desc, idx asc); its guard
+            // band (near ties of the pivot) stays available through sdpcs_last_band with scores = obj
             if (out_n) *out_n = ns;
             const char* h = (const char*)ctx->h_out;
-            const size_t kb = (size_t)std::max<i64>(k, 1) * 8;
+            const size_t cb = ctx->h_out_stride;
             for (i64 i = 0; i < ns; ++i) {
                 if (out_idx) out_idx[i] = sidx[i];
                 if (out_score) out_score[i] = sobj[i] + ctx->params.big_m;
             }
-            if (out_lam) memcpy(out_lam, h + sizeof(SelState) + 2 * kb, ns * 8);
-            if (out_obj) memcpy(out_obj, h + sizeof(SelState) + 3 * kb, ns * 8);
+            if (out_lam) memcpy(out_lam, h + 2 * cb, ns * 8);
+            if (out_obj) memcpy(out_obj, h + 3 * cb, ns * 8);
         } else {
             // pass 2: final measure of cut_select_qp.py:603-625
             if ((rc = topk_device(ctx, 4, k, pobj, pidx, all_walked ? 1 : 0))) return rc;
@@ -1108,7 +1203,7 @@ extern "C" int sdpcs_merge_topk(sdpcs_ctx* ctx, int64_t m, const double* score, 
     if (obj2) CU(cudaMemcpyAsync(d_obj2, obj2, m * 8, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(d_idx, idx, m * 8, cudaMemcpyHostToDevice, ctx->stream));
     k_merge_keys<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(m, d_score, obj2 ? d_obj2 : nullptr, d_k1, d_k2);
-    k_rank_sort<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(nullptr, m, d_k1, d_k2, d_idx, d_s1, d_s2, d_si);
+    k_rank_sort<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(nullptr, m, m, d_k1, d_k2, d_idx, d_s1, d_s2, d_si);
     CU(cudaGetLastError());
     std::vector<i64> sorted_idx(m), in_idx(idx, idx + m);
     CU(cudaMemcpyAsync(sorted_idx.data(), d_si, m * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1348,7 +1443,7 @@ extern "C" int sdpcs_triangles(sdpcs_ctx* ctx, const double* vars_values, int64_
     const i64 T = (i64)binom_small(ctx->n, 3), NK = 4 * T;
     kmax = std::min<i64>(kmax, NK);
     if ((rc = ensure_dev(ctx, ctx->d_key1, ctx->key_cap, NK))) return rc;
-    if ((rc = ensure_out(ctx, std::max<i64>(kmax, 1)))) return rc;
+    if ((rc = ensure_out(ctx, sel_capacity(ctx, kmax)))) return rc;
     CU(cudaMemsetAsync(ctx->d_tri_counters, 0, 2 * sizeof(unsigned long long), ctx->stream));
     TriArgs ta;
     ta.n = ctx->n; ta.T = T; ta.X = ctx->d_vars; ta.x = ctx->d_vars + (size_t)ctx->n * (ctx->n + 1) / 2;
@@ -1362,15 +1457,14 @@ extern "C" int sdpcs_triangles(sdpcs_ctx* ctx, const double* vars_values, int64_
     i64 m = 0;
     unsigned long long counters[2] = {0, 0};
     if (kmax > 0) {
-        if ((rc = run_select(ctx, ctx->d_key1, nullptr, nullptr, NK, 0, kmax))) return rc;
+        KeySrc ks;
+        memset(&ks, 0, sizeof(ks));
+        ks.key1 = ctx->d_key1; ks.N = NK; ks.base = 0;
+        if ((rc = run_select_t<0>(ctx, ks, kmax))) return rc;
         // unpack into the output scratch arrays (reuse d_c_* as typed outputs)
         i64* d_rank = ctx->d_c_idx; double* d_viol = ctx->d_o_score;
         int8_t* d_type = (int8_t*)ctx->d_c_k1; int8_t* d_dens = (int8_t*)ctx->d_c_k2;
-        // m is only known on the device: unpack kmax slots, copy back the valid prefix
-        SelState hs;
-        CU(cudaMemcpyAsync(&hs, ctx->d_state, sizeof(SelState), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        m = std::min<i64>((i64)hs.out_count, kmax);
+        m = std::min<i64>(ctx->h_state->k_out, kmax);
         if (m > 0) {
             k_tri_unpack<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(m, ctx->d_s_k1, ctx->d_s_idx, d_rank, d_type, d_viol, d_dens);
             CU(cudaGetLastError());

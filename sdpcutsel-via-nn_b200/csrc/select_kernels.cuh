@@ -1,12 +1,17 @@
-// K5: deterministic top-k over resident scores.
+// K5: deterministic top-k over resident scores, with a near-tie guard band.
 // Replaces rank_list.sort(key=itemgetter(1), reverse=True) + prefix slicing (cut_select_qp.py:601, 625, 653-654,
 // consumer bound :718) and the triangle sort (:841-844).  Python's stable descending sort == order by
 // (score desc, original position asc); for the combined rule the "original position" of the second sort is the
 // order of the first one, i.e. (obj desc, agg_idx asc).  Both are expressed as a 3-level key
 //     (key1 desc, key2 desc, idx asc)        key = order-preserving u64 image of the FP64 score
-// and resolved exactly by an MSD radix select (11-bit digits) over key1, then -- only if the k-th place falls
-// inside a tie class -- over key2 and over idx restricted to that class.  Then the <= k winners are collected
-// and ordered by a rank-counting sort. Everything runs on the device; no host round trip inside a selection.
+//
+// Keys are never materialised: every pass recomputes them from the resident lam / obj arrays (8 or 16 B read per
+// candidate and pass, nothing written).  An MSD radix select (11-bit digits) narrows key1; as soon as the number of
+// keys at or above the current prefix fits the output buffers (normally after 2-3 passes) everything above the
+// prefix is collected and ordered by a rank-counting sort: the first k entries are the selection, the entries after
+// them are the near ties of the k-th score (guard band, SURVEY 7 hard part 1).  Only if a tie class of identical
+// key1 values is larger than the buffers does the select continue over key2 and idx restricted to that class
+// (exact 3-level threshold) -- then the band is reported as open.
 #pragma once
 #include "device_math.cuh"
 
@@ -16,103 +21,127 @@ constexpr int SEL_BINS = 2048;
 constexpr u64 IDX_TOP = (1ull << 44) - 1;   // level-2 key = IDX_TOP - idx (smaller idx first); idx < 2^44
 
 struct SelState {
-    u64 T[3];        // per-level thresholds of the k-th element
+    u64 T[3];        // per-level thresholds of the k-th element (exact path)
     u64 prefix;      // partial prefix of the level being resolved
     i64 need;        // elements still to take from the current tie class
     i64 n_valid;     // # key1 != 0
     i64 k_eff;       // min(k, n_valid)
-    i64 n_violated;  // counters filled by k_make_keys
+    i64 n_violated;  // counters of the first pass (strict thresholds)
     i64 n_strong;
     u64 max_pos_nonviol; // enc_key of the largest obj among candidates with obj > thres_min_opt that are NOT violated (0: none)
+    i64 n_unc_lam;   // candidates with |lam - thres_neg_eigval| <= guard_lam (classification inside the guard band)
+    i64 n_unc_obj;   // candidates with |obj - thres_min_opt| <= guard_obj
+    u64 collect_lo;  // early exit: every key1 >= collect_lo is collected
+    i64 n_collect;   // ... and this many there are
+    i64 k_out;       // winners = min(k_eff, collected)
+    i64 band_count;  // entries right after the winners whose key1 score lies within the guard band of the k-th score
+    u64 band_key;    // enc_key(score_k - delta)
+    int band_open;   // 1: near ties may exist that were not collected (band reaches below collect_lo / exact path)
     int level;
-    int done;
+    int done;        // 0 running, 1 exact thresholds T[0..2], 2 early exit (collect_lo)
     unsigned out_count;
     unsigned pad;
     unsigned hist[SEL_BINS];
 };
 
-struct KeyArgs {
+// Where the keys come from.  MODE 0: stored key1 array (triangles); MODE 1..4: computed from the resident scores
+//   1  feasibility: violated only, key -lam                                  (cut_select_qp.py:639-654)
+//   2  optimality:  all, key obj                                             (cut_select_qp.py:599-601)
+//   3  strong set:  obj > thres_min_opt and violated, key obj                (cut_select_qp.py:607-612)
+//   4  combined final: key1 = re-scored measure given the pivot, key2 = obj  (cut_select_qp.py:603-625)
+// With a guard (guard_lam / guard_obj > 0) modes 1 and 3 classify with the RELAXED thresholds lam < thr + guard_lam,
+// obj > thr - guard_obj, so that a candidate whose classification the reference's LAPACK / libm rounding could flip is
+// never excluded on the device; the counters stay strict and n_unc_* say how many such candidates exist.
+struct KeySrc {
+    const u64* key1;
+    const i64* idx;              // MODE 0: explicit idx or nullptr (idx = base + position)
     const double* lam;
     const double* obj;
-    i64 N;
-    i64 base;            // agg_idx of local element 0
-    int mode;            // 1 feas, 2 opt, 3 strong, 4 combined-final
-    double thr_eig, thr_opt, big_m;
+    i64 N, base;
+    double thr_eig, thr_opt, big_m, guard_lam, guard_obj;
     double pivot_obj; i64 pivot_idx; int all_walked;
-    u64* key1; u64* key2;
     SelState* st;
 };
 
-__global__ void __launch_bounds__(256) k_make_keys(KeyArgs a)
-{
-    i64 nv = 0, ns = 0;
+struct SelCounters {
+    i64 nvalid = 0, nv = 0, ns = 0, nul = 0, nuo = 0;
     u64 mx = 0;
-    auto make = [&](i64 i, double lam, double obj, u64& k1, u64& k2) {
-        bool viol = a.lam && lam < a.thr_eig;
-        bool pos = a.obj && obj > a.thr_opt;
-        nv += viol; ns += (viol && pos);
-        if (pos && !viol) { const u64 e = enc_key(obj); mx = e > mx ? e : mx; }
-        k1 = 0; k2 = 0;
-        switch (a.mode) {
-        case 1: k1 = viol ? enc_key(-lam) : 0; break;
-        case 2: k1 = enc_key(obj); break;
-        case 3: k1 = (viol && pos) ? enc_key(obj) : 0; break;
-        default: {
-            i64 idx = a.base + i;
-            bool walked = a.all_walked || obj > a.pivot_obj || (obj == a.pivot_obj && idx <= a.pivot_idx);
+};
+
+template <int MODE, bool COUNT>
+__device__ __forceinline__ void make_key(const KeySrc& s, i64 i, u64 a_bits, u64 b_bits, u64& k1, u64& k2, SelCounters& c)
+{
+    k2 = 0;
+    if (MODE == 0) {
+        k1 = a_bits;
+    } else {
+        const double lam = __longlong_as_double((long long)a_bits), obj = __longlong_as_double((long long)b_bits);
+        const bool has_lam = (MODE != 2), has_obj = (MODE != 1);
+        const bool viol = has_lam && lam < s.thr_eig, pos = has_obj && obj > s.thr_opt;
+        const bool viol_r = has_lam && lam < s.thr_eig + s.guard_lam, pos_r = has_obj && obj > s.thr_opt - s.guard_obj;
+        if (COUNT) {
+            c.nv += viol; c.ns += (viol && pos);
+            c.nul += has_lam && s.guard_lam > 0.0 && fabs(lam - s.thr_eig) <= s.guard_lam;
+            c.nuo += has_obj && s.guard_obj > 0.0 && fabs(obj - s.thr_opt) <= s.guard_obj;
+            if (pos && !viol) { const u64 e = enc_key(obj); c.mx = e > c.mx ? e : c.mx; }
+        }
+        if (MODE == 1) k1 = viol_r ? enc_key(-lam) : 0;
+        else if (MODE == 2) k1 = enc_key(obj);
+        else if (MODE == 3) k1 = (viol_r && pos_r) ? enc_key(obj) : 0;
+        else {
+            const i64 idx = s.base + i;
+            const bool walked = s.all_walked || obj > s.pivot_obj || (obj == s.pivot_obj && idx <= s.pivot_idx);
             double f = obj;
             if (walked) {
-                if (pos) f = viol ? obj + a.big_m : obj - a.big_m;   // cut_select_qp.py:611, 615
+                if (pos) f = viol ? obj + s.big_m : obj - s.big_m;   // cut_select_qp.py:611, 615
                 else if (viol) f = -lam;                             // cut_select_qp.py:620
             }
             k1 = enc_key(f); k2 = enc_key(obj);
-        } break;
         }
-    };
-    // 16-byte loads / stores, two pairs in flight per thread (HBM-bound pass: 16 B read + 8..16 B written per candidate)
+    }
+    if (COUNT) c.nvalid += (k1 != 0);
+}
+
+// Grid-stride walk over all candidates with 16-byte loads, 4 (one array) or 2 x 2 (two arrays) loads in flight per
+// thread: an HBM-bound pass needs that much memory-level parallelism.  f(i, key1, key2).
+template <int MODE, bool COUNT, typename F>
+__device__ __forceinline__ void sel_foreach(const KeySrc& s, SelCounters& c, F&& f)
+{
+    constexpr bool LA = (MODE == 1 || MODE >= 3), LB = (MODE == 2 || MODE >= 3);
+    constexpr int U = (MODE >= 3) ? 2 : 4;
     const i64 tid = (i64)blockIdx.x * blockDim.x + threadIdx.x, nthr = (i64)gridDim.x * blockDim.x;
-    const i64 N4 = a.N & ~(i64)3;
-    for (i64 i = tid * 2; i < N4; i += nthr * 4) {
-        double2 L[2], O[2];
+    const i64 N2 = s.N & ~(i64)1;
+    const ulonglong2 zero = make_ulonglong2(0, 0);
+    for (i64 i = tid * 2; i < N2; i += nthr * 2 * U) {
+        ulonglong2 A[U], B[U];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const i64 j = i + u * nthr * 2;
-            const bool in = j < N4;
-            L[u] = (in && a.lam) ? *reinterpret_cast<const double2*>(a.lam + j) : make_double2(0.0, 0.0);
-            O[u] = (in && a.obj) ? *reinterpret_cast<const double2*>(a.obj + j) : make_double2(0.0, 0.0);
+        for (int u = 0; u < U; ++u) {
+            const i64 j = i + (i64)u * nthr * 2;
+            const bool in = j < N2;
+            A[u] = zero; B[u] = zero;
+            if (MODE == 0 && in) A[u] = *reinterpret_cast<const ulonglong2*>(s.key1 + j);
+            if (LA && in) A[u] = *reinterpret_cast<const ulonglong2*>(s.lam + j);
+            if (LB && in) B[u] = *reinterpret_cast<const ulonglong2*>(s.obj + j);
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const i64 j = i + u * nthr * 2;
-            if (j >= N4) continue;
-            ulonglong2 K1, K2;
-            make(j, L[u].x, O[u].x, K1.x, K2.x);
-            make(j + 1, L[u].y, O[u].y, K1.y, K2.y);
-            *reinterpret_cast<ulonglong2*>(a.key1 + j) = K1;
-            if (a.key2) *reinterpret_cast<ulonglong2*>(a.key2 + j) = K2;
+        for (int u = 0; u < U; ++u) {
+            const i64 j = i + (i64)u * nthr * 2;
+            if (j >= N2) continue;
+            u64 k1, k2;
+            make_key<MODE, COUNT>(s, j, A[u].x, B[u].x, k1, k2, c);
+            f(j, k1, k2);
+            make_key<MODE, COUNT>(s, j + 1, A[u].y, B[u].y, k1, k2, c);
+            f(j + 1, k1, k2);
         }
     }
-    for (i64 i = N4 + tid; i < a.N; i += nthr) {
-        u64 k1, k2;
-        make(i, a.lam ? a.lam[i] : 0.0, a.obj ? a.obj[i] : 0.0, k1, k2);
-        a.key1[i] = k1;
-        if (a.key2) a.key2[i] = k2;
-    }
-    // block reduce the two counters
-    __shared__ i64 sh[2][8];
-    for (int o = 16; o; o >>= 1) {
-        nv += __shfl_xor_sync(0xffffffffu, nv, o); ns += __shfl_xor_sync(0xffffffffu, ns, o);
-        const u64 m2 = __shfl_xor_sync(0xffffffffu, mx, o);
-        mx = m2 > mx ? m2 : mx;
-    }
-    if ((threadIdx.x & 31) == 0 && mx) atomicMax((unsigned long long*)&a.st->max_pos_nonviol, (unsigned long long)mx);
-    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = nv; sh[1][threadIdx.x >> 5] = ns; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        i64 a0 = 0, a1 = 0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a0 += sh[0][w]; a1 += sh[1][w]; }
-        if (a0) atomicAdd((u64*)&a.st->n_violated, (u64)a0);
-        if (a1) atomicAdd((u64*)&a.st->n_strong, (u64)a1);
+    if ((s.N & 1) && tid == 0) {
+        const i64 j = s.N - 1;
+        u64 a = 0, b = 0, k1, k2;
+        if (MODE == 0) a = s.key1[j];
+        if (LA) a = (u64)__double_as_longlong(s.lam[j]);
+        if (LB) b = (u64)__double_as_longlong(s.obj[j]);
+        make_key<MODE, COUNT>(s, j, a, b, k1, k2, c);
+        f(j, k1, k2);
     }
 }
 
@@ -121,42 +150,35 @@ __global__ void k_sel_reset(SelState* st)
     for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x) st->hist[i] = 0;
     if (threadIdx.x == 0) {
         st->T[0] = st->T[1] = st->T[2] = 0; st->prefix = 0; st->need = 0; st->n_valid = 0; st->k_eff = 0;
-        st->n_violated = 0; st->n_strong = 0; st->max_pos_nonviol = 0; st->level = 0; st->done = 0; st->out_count = 0;
+        st->n_violated = 0; st->n_strong = 0; st->max_pos_nonviol = 0; st->n_unc_lam = 0; st->n_unc_obj = 0;
+        st->collect_lo = 0; st->n_collect = 0; st->k_out = 0; st->band_count = 0; st->band_key = 0; st->band_open = 0;
+        st->level = 0; st->done = 0; st->out_count = 0;
     }
 }
 
-struct SelArgs {
-    const u64* key1; const u64* key2; const i64* idx;  // idx == nullptr: idx = base + position
-    i64 N; i64 base; SelState* st;
-};
-
-__device__ __forceinline__ u64 level_key(const SelArgs& a, i64 i, int level)
-{
-    if (level == 0) return a.key1[i];
-    if (level == 1) return a.key2 ? a.key2[i] : 0;
-    return IDX_TOP - (u64)(a.idx ? a.idx[i] : a.base + i);
-}
+__device__ __forceinline__ u64 idx_key(const KeySrc& s, i64 i) { return IDX_TOP - (u64)(s.idx ? s.idx[i] : s.base + i); }
 
 // one radix pass: histogram of digit (key >> shift) & (2^width - 1) over elements still matching
-__global__ void __launch_bounds__(512) k_sel_hist(SelArgs a, int level, int shift, int width, int count_valid)
+template <int MODE, bool COUNT>
+__global__ void __launch_bounds__(512) k_sel_hist(KeySrc s, int level, int shift, int width)
 {
     __shared__ unsigned sh[SEL_BINS];
-    SelState* st = a.st;
+    SelState* st = s.st;
     if (st->done || st->level != level) return;
     for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     const u64 T0 = st->T[0], T1 = st->T[1], prefix = st->prefix;
     const int hs = shift + width;
     const unsigned mask = (1u << width) - 1;
-    i64 nvalid = 0;
+    SelCounters c;
     // run-length aggregation per thread: the leading digits (sign + exponent of an FP64 score) put almost every key
     // into the same two or three bins, and one shared-memory atomic per key would serialise on them
     unsigned run_bin = 0, run_cnt = 0;
-    auto take = [&](i64 i, u64 k1) {
-        if (count_valid) nvalid += (k1 != 0);
+    auto take = [&](i64 i, u64 k1, u64 k2) {
+        if (k1 == 0) return;
         if (level >= 1 && k1 != T0) return;
-        if (level == 2 && a.key2 && a.key2[i] != T1) return;
-        u64 key = (level == 0) ? k1 : level_key(a, i, level);
+        if (level == 2 && k2 != T1) return;
+        const u64 key = (level == 0) ? k1 : (level == 1) ? k2 : idx_key(s, i);
         if (hs < 64 && (key >> hs) != (prefix >> hs)) return;
         const unsigned bin = (unsigned)(key >> shift) & mask;
         if (bin == run_bin) ++run_cnt;
@@ -165,36 +187,34 @@ __global__ void __launch_bounds__(512) k_sel_hist(SelArgs a, int level, int shif
             run_bin = bin; run_cnt = 1;
         }
     };
-    // four 16-byte loads in flight per thread: one 8-byte load per thread and iteration leaves HBM latency-bound
-    const i64 tid = (i64)blockIdx.x * blockDim.x + threadIdx.x, nthr = (i64)gridDim.x * blockDim.x;
-    const i64 N8 = a.N & ~(i64)7;
-    for (i64 i = tid * 2; i < N8; i += nthr * 8) {
-        ulonglong2 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const i64 j = i + u * nthr * 2;
-            v[u] = (j < N8) ? *reinterpret_cast<const ulonglong2*>(a.key1 + j) : make_ulonglong2(0, 0);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const i64 j = i + u * nthr * 2;
-            if (j < N8) { take(j, v[u].x); take(j + 1, v[u].y); }
-        }
-    }
-    for (i64 i = N8 + tid; i < a.N; i += nthr) take(i, a.key1[i]);
+    sel_foreach<MODE, COUNT>(s, c, take);
     if (run_cnt) atomicAdd(&sh[run_bin], run_cnt);
     __syncthreads();
     for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x)
         if (sh[i]) atomicAdd(&st->hist[i], sh[i]);
-    if (count_valid) {
-        for (int o = 16; o; o >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
-        if ((threadIdx.x & 31) == 0 && nvalid) atomicAdd((u64*)&st->n_valid, (u64)nvalid);
+    if (COUNT) {
+        for (int o = 16; o; o >>= 1) {
+            c.nvalid += __shfl_xor_sync(0xffffffffu, c.nvalid, o); c.nv += __shfl_xor_sync(0xffffffffu, c.nv, o);
+            c.ns += __shfl_xor_sync(0xffffffffu, c.ns, o); c.nul += __shfl_xor_sync(0xffffffffu, c.nul, o);
+            c.nuo += __shfl_xor_sync(0xffffffffu, c.nuo, o);
+            const u64 m2 = __shfl_xor_sync(0xffffffffu, c.mx, o);
+            c.mx = m2 > c.mx ? m2 : c.mx;
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (c.nvalid) atomicAdd((u64*)&st->n_valid, (u64)c.nvalid);
+            if (c.nv) atomicAdd((u64*)&st->n_violated, (u64)c.nv);
+            if (c.ns) atomicAdd((u64*)&st->n_strong, (u64)c.ns);
+            if (c.nul) atomicAdd((u64*)&st->n_unc_lam, (u64)c.nul);
+            if (c.nuo) atomicAdd((u64*)&st->n_unc_obj, (u64)c.nuo);
+            if (c.mx) atomicMax((unsigned long long*)&st->max_pos_nonviol, (unsigned long long)c.mx);
+        }
     }
 }
 
-// digit decision after a pass (single block of SEL_BINS/2 threads)
+// digit decision after a pass (single block).  Level 0: as soon as the keys at or above the chosen prefix number at most
+// cap_exit, the select stops (done = 2) and everything >= prefix is collected.
 __global__ void __launch_bounds__(1024) k_sel_scan(SelState* st, int level, int shift, int width, int first_pass,
-                                                   int last_pass, int next_level, i64 k)
+                                                   int last_pass, int next_level, i64 k, i64 cap_exit)
 {
     __shared__ i64 suf[SEL_BINS + 1];
     if (st->done || st->level != level) return;
@@ -213,18 +233,18 @@ __global__ void __launch_bounds__(1024) k_sel_scan(SelState* st, int level, int 
         if (i1 < SEL_BINS) suf[i1] += v1;
         __syncthreads();
     }
-    __shared__ i64 need_s;
+    __shared__ i64 need_s, keff_s;
     if (threadIdx.x == 0) {
-        i64 need = st->need;
+        i64 need = st->need, ke = st->k_eff;
         if (first_pass && level == 0) {
-            i64 ke = k < st->n_valid ? k : st->n_valid;
+            ke = k < st->n_valid ? k : st->n_valid;
             st->k_eff = ke;
             need = ke;
         }
-        need_s = need;
+        need_s = need; keff_s = ke;
     }
     __syncthreads();
-    const i64 need = need_s;
+    const i64 need = need_s, keff = keff_s;
     if (need <= 0) {   // nothing to select
         if (threadIdx.x == 0) { st->done = 1; st->T[0] = ~0ull; st->T[1] = ~0ull; st->T[2] = ~0ull; }
         for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x) st->hist[i] = 0;
@@ -238,7 +258,10 @@ __global__ void __launch_bounds__(1024) k_sel_scan(SelState* st, int level, int 
             i64 cnt = incl - above;
             st->prefix = prefix;
             st->need = need2;
-            if (last_pass) {
+            const i64 total = (keff - need) + incl;          // # key1 >= prefix (its low bits are zero)
+            if (level == 0 && total <= cap_exit) {
+                st->collect_lo = prefix; st->n_collect = total; st->done = 2;
+            } else if (last_pass) {
                 st->T[level] = prefix;
                 if (need2 == cnt || next_level < 0) st->done = 1;   // whole tie class taken
                 else { st->level = next_level; st->prefix = 0; }
@@ -249,47 +272,41 @@ __global__ void __launch_bounds__(1024) k_sel_scan(SelState* st, int level, int 
     for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x) st->hist[i] = 0;
 }
 
-__global__ void __launch_bounds__(256) k_sel_collect(SelArgs a, i64 cap, u64* out_k1, u64* out_k2, i64* out_idx)
+template <int MODE>
+__global__ void __launch_bounds__(256) k_sel_collect(KeySrc s, i64 cap, u64* out_k1, u64* out_k2, i64* out_idx)
 {
-    SelState* st = a.st;
-    if (st->k_eff <= 0) return;
-    const u64 T0 = st->T[0], T1 = st->T[1], T2 = st->T[2];
-    auto take = [&](i64 i, u64 k1) {
-        if (k1 < T0 || k1 == 0) return;
-        u64 k2 = a.key2 ? a.key2[i] : 0;
-        i64 idx = a.idx ? a.idx[i] : a.base + i;
-        if (k1 == T0) {
-            if (k2 < T1) return;
-            if (k2 == T1 && (IDX_TOP - (u64)idx) < T2) return;
+    SelState* st = s.st;
+    if (!st->done || st->k_eff <= 0) return;
+    const bool early = st->done == 2;
+    const u64 lo = st->collect_lo, T0 = st->T[0], T1 = st->T[1], T2 = st->T[2];
+    SelCounters c;
+    auto take = [&](i64 i, u64 k1, u64 k2) {
+        if (k1 == 0) return;
+        const i64 idx = (MODE == 0 && s.idx) ? s.idx[i] : s.base + i;
+        if (early) {
+            if (k1 < lo) return;
+        } else {
+            if (k1 < T0) return;
+            if (k1 == T0) {
+                if (k2 < T1) return;
+                if (k2 == T1 && (IDX_TOP - (u64)idx) < T2) return;
+            }
         }
         unsigned p = atomicAdd(&st->out_count, 1u);
         if ((i64)p < cap) { out_k1[p] = k1; out_k2[p] = k2; out_idx[p] = idx; }
     };
-    const i64 tid = (i64)blockIdx.x * blockDim.x + threadIdx.x, nthr = (i64)gridDim.x * blockDim.x;
-    const i64 N8 = a.N & ~(i64)7;
-    for (i64 i = tid * 2; i < N8; i += nthr * 8) {
-        ulonglong2 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const i64 j = i + u * nthr * 2;
-            v[u] = (j < N8) ? *reinterpret_cast<const ulonglong2*>(a.key1 + j) : make_ulonglong2(0, 0);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const i64 j = i + u * nthr * 2;
-            if (j < N8) { take(j, v[u].x); take(j + 1, v[u].y); }
-        }
-    }
-    for (i64 i = N8 + tid; i < a.N; i += nthr) take(i, a.key1[i]);
+    sel_foreach<MODE, false>(s, c, take);
 }
 
-// rank-counting sort of the m <= cap winners by (k1 desc, k2 desc, idx asc)
-__global__ void __launch_bounds__(256) k_rank_sort(const SelState* st, i64 m_fixed, const u64* k1, const u64* k2,
+// rank-counting sort of the m <= cap collected entries by (k1 desc, k2 desc, idx asc)
+__global__ void __launch_bounds__(256) k_rank_sort(const SelState* st, i64 m_fixed, i64 cap, const u64* k1, const u64* k2,
                                                    const i64* idx, u64* s_k1, u64* s_k2, i64* s_idx)
 {
     __shared__ u64 t1[256], t2[256];
     __shared__ i64 ti[256];
-    const i64 m = st ? (i64)st->out_count : m_fixed;
+    if (st && !st->done) return;
+    i64 m = st ? (i64)st->out_count : m_fixed;
+    if (m > cap) m = cap;
     const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if ((i64)blockIdx.x * blockDim.x >= m) return;
     u64 a1 = 0, a2 = 0; i64 ai = 0;
@@ -310,11 +327,46 @@ __global__ void __launch_bounds__(256) k_rank_sort(const SelState* st, i64 m_fix
     if (i < m) { s_k1[pos] = a1; s_k2[pos] = a2; s_idx[pos] = ai; }
 }
 
-// final gather of the winners' scores
-__global__ void k_sel_gather(const SelState* st, const u64* s_k1, const i64* s_idx, i64 base, const double* lam,
+// After the sort: number of winners, and the guard band = entries after the k-th whose key1 score is >= score_k - delta.
+// delta < 0: no guard.  band_open = 1 when near ties may exist that were not collected.
+__global__ void k_sel_finish(SelState* st, const u64* s_k1, i64 cap, double delta)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    if (!st->done) return;
+    i64 m = (i64)st->out_count;
+    if (m > cap) m = cap;
+    const i64 k_out = st->k_eff < m ? st->k_eff : m;
+    st->k_out = k_out;
+    st->band_count = 0; st->band_open = 0; st->band_key = 0;
+    if (k_out <= 0 || delta < 0.0) return;
+    const double sk = dec_key(s_k1[k_out - 1]);
+    const u64 bk = enc_key(sk - delta);
+    st->band_key = bk;
+    i64 lo = k_out, hi = m;                     // first position in [k_out, m) with key < bk (sorted descending)
+    while (lo < hi) {
+        const i64 mid = (lo + hi) >> 1;
+        if (s_k1[mid] >= bk) lo = mid + 1; else hi = mid;
+    }
+    st->band_count = lo - k_out;
+    const bool more_valid = st->n_valid > m;
+    if (st->done == 2) st->band_open = (more_valid && bk < st->collect_lo) ? 1 : 0;
+    else st->band_open = more_valid ? 1 : 0;    // exact path: only the k winners were collected
+}
+
+// re-open an early-exit selection with a lower collection bound (the band reached below collect_lo)
+__global__ void k_sel_lower(SelState* st)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    if (st->done == 2 && st->band_open) { st->collect_lo = st->band_key; st->out_count = 0; }
+}
+
+// final gather of the collected entries' scores
+__global__ void k_sel_gather(const SelState* st, i64 cap, const u64* s_k1, const i64* s_idx, i64 base, const double* lam,
                              const double* obj, double* o_score, double* o_lam, double* o_obj)
 {
-    const i64 m = (i64)st->out_count;
+    if (!st->done) return;
+    i64 m = (i64)st->out_count;
+    if (m > cap) m = cap;
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (i64)gridDim.x * blockDim.x) {
         i64 loc = s_idx[i] - base;
         o_score[i] = dec_key(s_k1[i]);

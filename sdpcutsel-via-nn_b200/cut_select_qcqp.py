@@ -9,7 +9,7 @@ slicing (not re-sorted, :79), and cut generation that tells the two entry format
 import numpy as np
 
 from . import _capi, cover
-from .cut_select_qp import CutSolver
+from .cut_select_qp import B200CutSelection, CutSolver
 
 
 def _row_keys(idx):
@@ -18,6 +18,33 @@ def _row_keys(idx):
     for t in range(idx.shape[1]):
         k = (k << np.uint64(9)) | (idx[:, t].astype(np.int64) + 1).astype(np.uint64)
     return k
+
+
+def two_pattern_covers(solver, dim):
+    """cut_select_qcqp.py:314-334 for any solver object carrying the B200CutSelection surface: sets
+    solver._agg_list := P(E_m) intersected with P(E_0) (in P(E_m) order) and returns P(E_m) minus that intersection,
+    where P(E_0) is the cover of the objective pattern (_Q_adj) and P(E_m) that of objective + constraints (_Q_adj_cons)."""
+    B200CutSelection._get_sdp_vertex_cover(solver, dim)
+    agg_obj = solver._agg_list
+    Q_adj = solver._Q_adj
+    solver._Q_adj = solver._Q_adj_cons
+    try:
+        B200CutSelection._get_sdp_vertex_cover(solver, dim)
+    finally:
+        solver._Q_adj = Q_adj
+    agg_cons = solver._agg_list
+    n, Q_arr = solver._nb_vars, np.asarray(solver._Q_arr, dtype=np.float64)
+    empty = cover.AggList(n, dim, Q_arr, idx=np.zeros((0, dim), dtype=np.int16))
+    if agg_obj.is_all:                                   # every element of P(E_m) is in P(E_0)
+        solver._agg_list = agg_cons
+        return empty
+    cons_idx = agg_cons.idx if not agg_cons.is_all else \
+        _capi.unrank(n, dim, np.arange(len(agg_cons))).astype(np.int16)
+    # membership of every P(E_m) row in P(E_0): one 45-bit key per (-1 padded) index row instead of the reference's
+    # O(N^2) `el in agg_list` scans (cut_select_qcqp.py:322-331)
+    inter = np.isin(_row_keys(cons_idx), _row_keys(agg_obj.idx))
+    solver._agg_list = cover.AggList(n, dim, Q_arr, idx=np.ascontiguousarray(cons_idx[inter]))
+    return cover.AggList(n, dim, Q_arr, idx=np.ascontiguousarray(cons_idx[~inter]))
 
 
 class CutSolverQCQP(CutSolver):
@@ -30,27 +57,7 @@ class CutSolverQCQP(CutSolver):
         self._Q_adj_cons = Q_adj if Q_adj_cons is None else Q_adj_cons
 
     def __get_vertex_cover(self, dim):                       # -> _CutSolverQCQP__get_vertex_cover
-        """cut_select_qcqp.py:314-334: self._agg_list := P(E_m) intersected with P(E_0) (in P(E_m) order);
-        returns P(E_m) minus that intersection."""
-        super(CutSolverQCQP, self)._get_sdp_vertex_cover(dim)
-        agg_obj = self._agg_list
-        Q_adj = self._Q_adj
-        self._Q_adj = self._Q_adj_cons
-        super(CutSolverQCQP, self)._get_sdp_vertex_cover(dim)
-        agg_cons = self._agg_list
-        self._Q_adj = Q_adj
-        n, Q_arr = self._nb_vars, np.asarray(self._Q_arr, dtype=np.float64)
-        empty = cover.AggList(n, dim, Q_arr, idx=np.zeros((0, dim), dtype=np.int16))
-        if agg_obj.is_all:                                   # every element of P(E_m) is in P(E_0)
-            self._agg_list = agg_cons
-            return empty
-        cons_idx = agg_cons.idx if not agg_cons.is_all else \
-            _capi.unrank(n, dim, np.arange(len(agg_cons))).astype(np.int16)
-        # membership of every P(E_m) row in P(E_0): one 45-bit key per (-1 padded) index row instead of the reference's
-        # O(N^2) `el in agg_list` scans (cut_select_qcqp.py:322-331)
-        inter = np.isin(_row_keys(cons_idx), _row_keys(agg_obj.idx))
-        self._agg_list = cover.AggList(n, dim, Q_arr, idx=np.ascontiguousarray(cons_idx[inter]))
-        return cover.AggList(n, dim, Q_arr, idx=np.ascontiguousarray(cons_idx[~inter]))
+        return two_pattern_covers(self, dim)
 
     def get_vertex_cover(self, dim):
         return self.__get_vertex_cover(dim)

@@ -16,12 +16,17 @@ but every score, selection and cut is computed by libsdpcutsel on the GPU.  The 
 Narrowing: the ranked list a selection returns is only ever consumed as a prefix of length
 <= sel_size <= _SDP_CUTS_PER_ROUND_MAX, so strat 1 / 2 return the first ``_RANK_PREFIX`` (= 5000, or sel_size if
 larger) entries of the reference's list instead of all N; ``RankList.n_total`` / ``n_violated`` keep the counts.
+Near ties (SURVEY.md 7): the device returns the winners plus every candidate within a guard band of the k-th score;
+runs of entries closer than the guard are re-scored with the reference's own arithmetic (numpy eigvalsh / the generated
+NN function, ``neartie.py``) and re-sorted, so that the prefix equals the reference's also on LP vertices where
+thousands of candidates tie; ``RankList.degenerate`` / ``n_near_ties`` report what happened.
 Out of scope and raising NotImplementedError: strat 3 / -1 (Mosek exact SDP), strat 5 (random shuffle),
 ch_ext 1 / 2 (chompack chordal extension).
 """
 import numpy as np
 
-from . import _capi, cover, nn_weights
+from . import _capi, cover, neartie, nn_weights
+from .distributed import ShardedSelector
 
 try:  # the cut sink type of the reference (cut_select_qp.py:747); a plain container when CPLEX is absent
     from cplex import SparsePair
@@ -32,9 +37,13 @@ except ImportError:  # pragma: no cover - depends on the environment
 
 
 class RankList(list):
-    """Prefix of the reference's sorted rank_list plus the totals the full list would have had."""
+    """Prefix of the reference's sorted rank_list plus the totals the full list would have had.
+    degenerate: 0 = no near tie touched the prefix, 1 = near ties re-scored with the reference's arithmetic and resolved,
+    2 = more near ties than the guard band holds (order inside them is the device's own); n_near_ties = entries re-scored."""
     n_total = 0
     n_violated = 0
+    degenerate = 0
+    n_near_ties = 0
 
 
 class _RowSink(object):
@@ -90,11 +99,20 @@ class B200CutSelection(object):
         self._agg_list, self._tri_engine, self._dense_engine = [], None, None
 
     # -- engines ---------------------------------------------------------------------------------------
+    _GUARD_LAM = 10 ** (-12)     # near-tie guard on eigenvalue scores (device vs LAPACK differ by <= ~1e-14)
+    _GUARD_OBJ_REL = 4 * 10 ** (-12)   # near-tie guard on optimality measures, times rho * max|Q_arr| (the scale of max_elem)
+
+    def _guards(self):
+        Q_arr = np.asarray(self._Q_arr, dtype=np.float64)
+        scale = float(np.abs(Q_arr).max()) if Q_arr.size else 1.0
+        return float(self._GUARD_LAM), max(10 ** (-12), self._GUARD_OBJ_REL * max(self._dim, 2) * max(scale, 1.0))
+
     def _new_engine(self):
         eng = _capi.Engine(self._DEVICE)
+        g_lam, g_obj = self._guards()
         eng.set_params(thres_min_opt=float(self._THRES_MIN_OPT), thres_neg_eigval=float(self._THRES_NEG_EIGVAL),
                        big_m=float(self._BIG_M), thres_tri_viol=float(self._THRES_TRI_VIOL),
-                       thres_tri_dense=int(self._THRES_TRI_DENSE))
+                       thres_tri_dense=int(self._THRES_TRI_DENSE), guard_lam=g_lam, guard_obj=g_obj)
         for d, blob in self._blobs.items():
             eng.set_weights(d, blob)
         eng.set_instance(self._nb_vars, np.asarray(self._Q_arr, dtype=np.float64))
@@ -103,7 +121,9 @@ class B200CutSelection(object):
     def _engine_for(self, agg_list):
         """The device context that holds `agg_list` as its cover (the caller may re-point self._agg_list)."""
         if not isinstance(agg_list, cover.AggList):
-            raise TypeError("self._agg_list must come from _get_sdp_vertex_cover (an AggList)")
+            # a plain list in the reference's own tuple format (e.g. built by the reference's
+            # CutSolverQCQP.__get_vertex_cover, cut_select_qcqp.py:319-333): adopt its index lists
+            agg_list = self._adopt_agg_list(agg_list)
         if agg_list._engine is None:
             eng = self._new_engine()
             if agg_list.is_all:
@@ -112,6 +132,22 @@ class B200CutSelection(object):
                 eng.set_cover_list(agg_list.dim, agg_list.idx, agg_list.offset)
             agg_list._engine = eng
         return agg_list._engine
+
+    def _adopt_agg_list(self, plain):
+        """AggList view of a plain list of reference tuples (setInds, Xarr_inds, Q_slice, max_elem); cached per list object."""
+        cache = self.__dict__.setdefault("_adopted", {})
+        hit = cache.get(id(plain))
+        if hit is not None and hit[0] is plain and len(plain) == len(hit[1]):
+            return hit[1]
+        dim = max([self._dim] + [len(el[0]) for el in plain]) if len(plain) else max(self._dim, 2)
+        idx = np.full((len(plain), dim), -1, dtype=np.int16)
+        for i, el in enumerate(plain):
+            idx[i, :len(el[0])] = el[0]
+        agg = cover.AggList(self._nb_vars, dim, np.asarray(self._Q_arr, dtype=np.float64), idx=idx)
+        if len(cache) > 8:
+            cache.clear()
+        cache[id(plain)] = (plain, agg)
+        return agg
 
     # -- reference surface -----------------------------------------------------------------------------
     def _load_neural_nets(self):
@@ -130,11 +166,16 @@ class B200CutSelection(object):
         n = self._nb_vars
         self._agg_list = None
         Q_arr = np.asarray(self._Q_arr, dtype=np.float64)
-        if ch_ext == -1:   # P^E+: all subsets (the reference implements dim 3 only, cut_select_qp.py:451-455)
+        if dim == 3 and ch_ext not in (0, -1):
+            # the reference's dim-3 branch knows ch_ext 0, 1, 2, -1 only (cut_select_qp.py:405-455): anything else leaves
+            # idx_list empty
+            agg = cover.AggList(n, dim, Q_arr, idx=np.zeros((0, dim), dtype=np.int16))
+        elif dim == 3 and ch_ext == -1 and n >= 3:
+            # P^E+_3: all triples (cut_select_qp.py:451-455); for dim 4 / 5 the reference ignores ch_ext and builds P^E
             agg = cover.AggList(n, dim, Q_arr, n_all=_capi.binom(n, dim))
         else:
             adj = _as_dense_adj(self._Q_adj, n)
-            if _is_complete(adj):      # dense pattern: P^E_dim is all subsets in lex order -> nothing to store
+            if n >= dim and _is_complete(adj):   # dense pattern: P^E_dim is all subsets in lex order -> nothing to store
                 agg = cover.AggList(n, dim, Q_arr, n_all=_capi.binom(n, dim))
             else:
                 # the nested clique loops (cut_select_qp.py:401-522) run on the device; the index tuples come back once
@@ -153,7 +194,7 @@ class B200CutSelection(object):
             raise NotImplementedError("strat %d (exact SDP via Mosek / random / figure 8) is outside the GPU hot path" % strat)
         if strat not in (1, 2, 4):
             raise ValueError("strat must be 1 (feasibility), 2 (optimality) or 4 (combined)")
-        agg = self._agg_list
+        agg = self._agg_view()
         eng = self._engine_for(agg)
         N = len(agg)
         sel_size = min(sel_size, N)                                   # cut_select_qp.py:550
@@ -166,10 +207,11 @@ class B200CutSelection(object):
         else:
             strat_eff = strat
             k = sel_size if strat == 4 else min(N, max(sel_size, self._RANK_PREFIX))
-        res = eng.select(strat_eff, vars_values, k)
+        res = self._select_resolved(eng, agg, strat_eff, vars_values, k)
         out = RankList()
         out.n_total = N
         out.n_violated = int(res["counts"][1])
+        out.degenerate, out.n_near_ties = int(res["degenerate"]), int(res["n_near_ties"])
         X_vals, x_vals = vars_values[:nb_lifted], vars_values[nb_lifted:]
         sets = self._sets_of(agg, res["idx"])
         if strat_eff == 1:
@@ -183,39 +225,83 @@ class B200CutSelection(object):
             return (int(res["new_strat"]), out)                                    # cut_select_qp.py:629-630
         return out
 
+    def _select_resolved(self, eng, agg, strat, vars_values, k):
+        """Device selection (winners + guard band) followed by the near-tie resolution of neartie.resolve.  If re-scoring
+        drops entries of the strong list of the combined rule (classified differently by the reference's arithmetic), the
+        selection is repeated deeper."""
+        g_lam, g_obj = float(eng.params.guard_lam), float(eng.params.guard_obj)
+        sel = ShardedSelector(eng, local=True)
+        rescorer = neartie.Rescorer(self._nb_vars, self._Q_arr, vars_values, self._blobs,
+                                    lambda idx: self._set_rows(agg, idx), thr_eig=float(self._THRES_NEG_EIGVAL),
+                                    thr_opt=float(self._THRES_MIN_OPT), big_m=float(self._BIG_M))
+        k_try, vv = k, vars_values
+        for _ in range(4):
+            raw = sel.select(strat, vv, k_try)
+            res = neartie.resolve(raw, k, rescorer, g_lam, g_obj)
+            short = res.get("short", 0)
+            if not short or raw["idx"].size < k_try:
+                break
+            k_try, vv = min(len(agg), k_try + short + 64), None       # the LP point is resident now
+        if res.get("short", 0) and raw["idx"].size >= k_try:
+            res["degenerate"] = 2
+        return res
+
+    def _set_rows(self, agg, idx):
+        """(m, dim) int array of index tuples, -1 padded, for candidate indices idx."""
+        idx = np.asarray(idx, dtype=np.int64)
+        if agg.is_all:
+            if idx.size == 0:
+                return np.zeros((0, agg.dim), dtype=np.int64)
+            return _capi.unrank(agg.n, agg.dim, idx - agg.offset).astype(np.int64)
+        return agg.idx[idx - agg.offset].astype(np.int64)
+
     def _sets_of(self, agg, idx):
         if len(idx) == 0:
             return []
-        if agg.is_all:
-            return [[int(v) for v in r] for r in _capi.unrank(agg.n, agg.dim, np.asarray(idx) - agg.offset)]
-        return [[int(v) for v in agg.idx[i - agg.offset] if v >= 0] for i in idx]
+        rows = self._set_rows(agg, idx).tolist()
+        return rows if agg.is_all else [[v for v in r if v >= 0] for r in rows]
+
+    def _agg_view(self):
+        """self._agg_list as an AggList (the caller may have re-pointed it to a plain list in the reference's format)."""
+        agg = self._agg_list
+        return agg if isinstance(agg, cover.AggList) else self._adopt_agg_list(agg)
+
+    def _any_engine(self):
+        """A device context of the current instance for calls that do not need a cover (cuts, single eigen-decompositions)."""
+        if isinstance(self._agg_list, cover.AggList) or (isinstance(self._agg_list, list) and len(self._agg_list)):
+            return self._engine_for(self._agg_list)
+        eng = getattr(self, "_misc_engine", None)
+        if eng is None or eng.n != self._nb_vars or getattr(self, "_misc_engine_Q", None) is not self._Q_arr:
+            self._misc_engine, self._misc_engine_Q = self._new_engine(), self._Q_arr
+        return self._misc_engine
 
     def _gen_eigcuts_selected(self, strat, sel_size, rank_list, strong_only=False, vars_values=None):
         opt_sel, feas_sel, rand_sel = (strat in [2, 3, 4, -1]), (strat == 1), (strat == 5)
         if rand_sel:
             raise NotImplementedError("random selection (strat 5) is outside the GPU hot path")
-        my_prob, nb_lifted = self._my_prob, self._nb_lifted
+        my_prob = self._my_prob
         sel_size = min(sel_size, len(rank_list))                                   # cut_select_qp.py:713
         if vars_values is None:
             vars_values = self._last_vars_values                                   # opt entries carry their own point
-        sets = []
-        for ix in range(sel_size):
-            entry = rank_list[ix]
-            if opt_sel:
-                idx, diff = entry[0], entry[1]
-                if strong_only and diff <= 0:                                      # cut_select_qp.py:725-726
+        packed = None
+        if opt_sel:
+            idxs = []
+            for ix in range(sel_size):
+                entry = rank_list[ix]
+                if strong_only and entry[1] <= 0:                                  # cut_select_qp.py:725-726
                     break
-                sets.append(self._sets_of(self._agg_list, [idx])[0])
-            else:
-                sets.append(list(entry[0]))
-        coeffs_sdp, rhs_sdp, senses_sdp = [], [], []
-        if sets:
+                idxs.append(entry[0])
+            if idxs:
+                packed = self._set_rows(self._agg_view(), idxs).astype(np.int16)
+        elif sel_size:
+            sets = [rank_list[ix][0] for ix in range(sel_size)]
             dim = max(self._dim, max(len(s) for s in sets))
             packed = np.full((len(sets), dim), -1, dtype=np.int16)
             for i, s in enumerate(sets):
                 packed[i, :len(s)] = s
-            eng = self._engine_for(self._agg_list) if isinstance(self._agg_list, cover.AggList) else self._new_engine()
-            csr = eng.gen_cuts_csr(dim, packed, vars_values)       # violated cuts only (eigvals[0] < _THRES_NEG_EIGVAL)
+        coeffs_sdp, rhs_sdp, senses_sdp = [], [], []
+        if packed is not None and packed.shape[0]:
+            csr = self._any_engine().gen_cuts_csr(packed.shape[1], packed, vars_values)   # violated cuts only (eigvals[0] < _THRES_NEG_EIGVAL)
             if _add_rows_csr(my_prob, csr):
                 return len(csr["rhs"])
             coeffs_sdp, rhs_sdp = _sparse_pairs(csr), csr["rhs"].tolist()
@@ -224,14 +310,16 @@ class B200CutSelection(object):
         return len(rhs_sdp)
 
     def _get_eigendecomp(self, dim_subpr, curr_pt, X_slice, ev_yes):
-        eng = self._engine_for(self._agg_list) if isinstance(self._agg_list, cover.AggList) else self._new_engine()
-        vals, vecs = eng.eigendecomp(dim_subpr, curr_pt, X_slice, want_vecs=bool(ev_yes))
+        vals, vecs = self._any_engine().eigendecomp(dim_subpr, curr_pt, X_slice, want_vecs=bool(ev_yes))
         return (vals, vecs) if ev_yes else vals
 
     def _dense_eigcuts(self, vars_values=None):
         """Strat 0 (cut_select_qp.py:757-786): one dense row per negative eigenvalue of the full [1 x^T; x X]."""
-        if getattr(self, "_dense_engine", None) is None:
-            self._dense_engine = self._new_engine()
+        eng = getattr(self, "_dense_engine", None)
+        # the reference re-uses one solver object for many instances (generate_figs_tables.py:319-373): the context is
+        # only valid for the instance it was created for
+        if eng is None or eng.n != self._nb_vars or getattr(self, "_dense_engine_Q", None) is not self._Q_arr:
+            self._dense_engine, self._dense_engine_Q = self._new_engine(), self._Q_arr
         d = self._dense_engine.dense_eigcuts(vars_values)
         nb, width = d["val"].shape
         csr = dict(rowptr=np.arange(nb + 1, dtype=np.int64) * width, ind=np.tile(d["ind"], nb), val=d["val"].ravel(), rhs=d["rhs"])
@@ -250,7 +338,7 @@ class B200CutSelection(object):
         self._rank_list_tri, self._idx_list_tri = None, None     # the per-triple lists are not materialised
 
     def _tri_separate(self, sel_size, vars_values):
-        if self._tri_engine is None:
+        if self._tri_engine is None or self._tri_engine.n != self._nb_vars:
             self._tri_preprocess()
         n, nb_lifted, my_prob = self._nb_vars, self._nb_lifted, self._my_prob
         t = self._tri_engine.triangles(vars_values, self._TRI_CUTS_PER_ROUND_MAX)

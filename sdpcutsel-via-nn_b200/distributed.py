@@ -1,13 +1,20 @@
 """Multi-GPU selection: the candidate index space is cut into contiguous rank ranges, one per process/GPU
 (torch.distributed, NCCL over NVLink on the B200 box, gloo in CPU tests). Each rank scores its shard and takes a
-local top-k; one small all-gather (k x 4 doubles per rank) plus an identical merge on every rank gives the
-global selection. The combined strategy needs the global pivot, hence two gather rounds and one
-all-reduce of three counters.
+local top-k; one small all-gather (k + B rows of 4 doubles per rank) plus an identical merge on every rank gives the
+global selection. The combined strategy needs the global pivot, hence up to two gather rounds; the
+counters ride in the header rows.
+
+The selector returns the k winners AND their guard band (the candidates ranked after the k-th whose score is within the
+near-tie guard of the k-th score, sdpcs_last_band) so that ``neartie.resolve`` can reproduce the reference's order where
+scores agree to rounding noise.  With one process the band is whatever the device collected (up to band_cap entries);
+across processes each rank contributes at most ``BAND_ROWS`` band rows to the exchange.
 """
 import os
 import time
 
 import numpy as np
+
+BAND_ROWS = 64          # band rows per rank in the exchange (a rank's band only matters when its k-th score is the global one)
 
 
 def shard_range(N, world, rank):
@@ -22,18 +29,23 @@ def shard_cover(engine, world, rank):
     return b, e
 
 
+_EMPTY_BAND = dict(n_band=0, band_open=0, n_unc_lam=0, n_unc_obj=0)
+
+
 class ShardedSelector(object):
     """engine: an _capi.Engine (or any object with score/topk/counts/merge_topk) whose cover is this rank's shard."""
 
-    def __init__(self, engine, group=None, device=None):
+    def __init__(self, engine, group=None, device=None, local=False):
         self.eng = engine
         self.group = group
         self.device = device
-        try:
-            import torch.distributed as dist
-            self.dist = dist if dist.is_available() and dist.is_initialized() else None
-        except ImportError:
-            self.dist = None
+        self.dist = None
+        if not local:                      # local: one process owns the whole cover (the drop-in CutSolver)
+            try:
+                import torch.distributed as dist
+                self.dist = dist if dist.is_available() and dist.is_initialized() else None
+            except ImportError:
+                self.dist = None
         self.world = self.dist.get_world_size(group) if self.dist else 1
         self.prof = {} if os.environ.get("SDPCS_DIST_PROFILE") else None     # phase -> accumulated seconds (host clock)
 
@@ -55,66 +67,100 @@ class ShardedSelector(object):
         self.dist.all_gather_into_tensor(out, t, group=self.group)
         return out.cpu().numpy().reshape((self.world,) + tuple(t.shape))
 
-    def _allreduce_sum(self, arr):
-        if self.world == 1:
-            return arr
-        import torch
-        t = torch.from_numpy(np.ascontiguousarray(arr))
-        if self.device is not None:
-            t = t.to(self.device)
-        self.dist.all_reduce(t, group=self.group)
-        return t.cpu().numpy()
+    def _band(self):
+        """Guard band + counters of the engine's last top-k pass (engines without a guard report none)."""
+        if not hasattr(self.eng, "last_band"):
+            z = np.zeros(0)
+            return dict(idx=z.astype(np.int64), score=z, lam=z, obj=z, **_EMPTY_BAND)
+        return self.eng.last_band(None if self.world == 1 else BAND_ROWS)
 
-    def _gather_merge(self, k, idx, score, lam, obj, use_obj2, counts=None, extra=0.0):
-        """All-gather of the local lists (k + 2 rows of 4 doubles per rank) and the identical merge on every rank.
-        Row 0 carries the list length and, when given, the rank's three counters (they ride along instead of needing
-        their own all-reduce), row 1 one more statistic (`extra`, reduced with max); returns (idx, score, lam, obj,
-        summed counters or None, max of extra)."""
-        m = idx.shape[0]
-        pack = np.zeros((k + 2, 4))
-        pack[0, 0] = m
+    def _guard_of(self, mode):
+        p = getattr(self.eng, "params", None)
+        if p is None:
+            return 0.0
+        return float(p.guard_lam if mode == 1 else p.guard_obj)
+
+    def _gather_merge(self, mode, k, top, band, use_obj2, counts=None, extra=0.0):
+        """All-gather of the local lists and the identical merge on every rank.  `top` = (idx, score, lam, obj) of the
+        local winners, `band` the local guard band.  Returns (winners, band dict, summed counters or None, max of extra).
+        Row 0 of a rank's block carries the list lengths and, when given, the rank's three counters (they ride along
+        instead of needing their own all-reduce); row 1 `extra` (reduced with max) and the guard counters."""
+        idx, score, lam, obj = top
+        if self.world == 1:
+            return top, band, (np.asarray(counts, dtype=np.int64) if counts is not None else None), float(extra)
+        m, mb = idx.shape[0], band["idx"].shape[0]
+        pack = np.zeros((k + 2 + BAND_ROWS, 4))
+        pack[0, 0] = m + mb
         if counts is not None:
             pack[0, 1:4] = counts          # < 2^44: exact in float64
-        pack[1, 0] = extra
-        pack[2:m + 2, 0] = idx            # agg_idx < 2^44: exact in float64
-        pack[2:m + 2, 1] = score
-        pack[2:m + 2, 2] = lam
-        pack[2:m + 2, 3] = obj
+        pack[1] = (extra, band["n_unc_lam"], band["n_unc_obj"], 1.0 if (band["band_open"] or band["n_band"] > mb) else 0.0)
+        rows = pack[2:2 + m + mb]
+        rows[:, 0] = np.concatenate([idx, band["idx"]])     # agg_idx < 2^44: exact in float64
+        rows[:, 1] = np.concatenate([score, band["score"]])
+        rows[:, 2] = np.concatenate([lam, band["lam"]])
+        rows[:, 3] = np.concatenate([obj, band["obj"]])
         allp = self._allgather(pack)
         tot = allp[:, 0, 1:4].sum(axis=0).astype(np.int64) if counts is not None else None
         ext = float(allp[:, 1, 0].max())
-        rows = np.concatenate([allp[r, 2:int(allp[r, 0, 0]) + 2] for r in range(self.world)], axis=0)
+        lens = [int(allp[r, 0, 0]) for r in range(self.world)]
+        rows = np.concatenate([allp[r, 2:lens[r] + 2] for r in range(self.world)], axis=0)
+        gb = dict(n_unc_lam=int(allp[:, 1, 1].sum()), n_unc_obj=int(allp[:, 1, 2].sum()), band_open=0, n_band=0)
+        z = np.zeros(0)
         if rows.shape[0] == 0:
-            z = np.zeros(0)
-            return z.astype(np.int64), z, z, z, tot, ext
+            gb.update(idx=z.astype(np.int64), score=z, lam=z, obj=z)
+            return (z.astype(np.int64), z, z, z), gb, tot, ext
         gidx = rows[:, 0].astype(np.int64)
-        if self.world == 1:
-            perm = np.arange(min(k, rows.shape[0]))
+        perm = self.eng.merge_topk(rows[:, 1], rows[:, 3] if use_obj2 else None, gidx, rows.shape[0])
+        kk = min(k, perm.size)
+        win = perm[:kk]
+        # global band: merged entries after the k-th within the guard of the k-th score; it is complete unless a rank whose
+        # list ends inside the band had more near ties than it could send
+        delta = self._guard_of(mode)
+        rest = perm[kk:]
+        if kk > 0 and rest.size:
+            sk = rows[win[-1], 1]
+            inb = rest[rows[rest, 1] >= sk - delta]
+            for r in range(self.world):
+                if lens[r] and allp[r, 1, 3] and allp[r, 2 + lens[r] - 1, 1] >= sk - delta:
+                    gb["band_open"] = 1
         else:
-            perm = self.eng.merge_topk(rows[:, 1], rows[:, 3] if use_obj2 else None, gidx, k)
-        return gidx[perm], rows[perm, 1], rows[perm, 2], rows[perm, 3], tot, ext
+            inb = rest[:0]
+            gb["band_open"] = int(allp[:, 1, 3].max()) if kk < k else 0
+        gb.update(idx=gidx[inb], score=rows[inb, 1], lam=rows[inb, 2], obj=rows[inb, 3], n_band=int(inb.size))
+        return (gidx[win], rows[win, 1], rows[win, 2], rows[win, 3]), gb, tot, ext
 
     # -- public ------------------------------------------------------------------------------------
     def select(self, strat, vars_values, k, n_total=None):
-        """Global selection over all shards. Returns dict(idx, score, lam, obj, counts, new_strat) -- identical
-        on every rank. vars_values None = LP point already resident on the device."""
+        """Global selection over all shards. Returns dict(idx, score, lam, obj, counts, new_strat, band, guard, strat, path,
+        pivot) -- identical on every rank. vars_values None = LP point already resident on the device.  `band` holds the
+        near ties that follow the k winners, `guard` = dict(n_band, band_open, n_unc_lam, n_unc_obj), `path` = the top-k
+        mode that produced the list (3: strong-prefix shortcut of the combined rule, scores already + big_m)."""
         eng = self.eng
         k = int(k)
         if strat not in (1, 2, 4):
             raise ValueError("strat must be 1, 2 or 4")
         t = time.perf_counter()
         eng.score(vars_values, 1 if strat == 1 else 2 if strat == 2 else 3)
+
+        def pack(top, band, counts, new_strat, path, pivot=None):
+            gi, gs, gl, go = top
+            guard = {key: int(band[key]) for key in ("n_band", "band_open", "n_unc_lam", "n_unc_obj")}
+            return dict(idx=gi, score=gs, lam=gl, obj=go, counts=counts, new_strat=new_strat, strat=strat, path=path, pivot=pivot,
+                        band={key: band[key] for key in ("idx", "score", "lam", "obj")}, guard=guard)
+
         if strat != 4:
-            idx, sc, lam, obj = eng.topk(strat, k)
+            top = eng.topk(strat, k)
+            band = self._band()
             t = self._t("score+topk", t)
-            gi, gs, gl, go, counts, _ = self._gather_merge(k, idx, sc, lam, obj, False, eng.counts())
+            top, band, counts, _ = self._gather_merge(strat, k, top, band, False, eng.counts())
             self._t("exchange+merge", t)
-            return dict(idx=gi, score=gs, lam=gl, obj=go, counts=counts, new_strat=strat)
-        idx, sc, lam, obj = eng.topk(3, k)
+            return pack(top, band, counts, strat, strat)
+        top = eng.topk(3, k)
+        band = self._band()
         t = self._t("score+topk1", t)
         # the pivot of the combined rule needs k <= N; N is only known after the exchange, so gather k rows and cut after
         mpn = eng.max_pos_nonviolated() if hasattr(eng, "max_pos_nonviolated") else np.inf
-        si, ss, sl, so, counts, mpn = self._gather_merge(k, idx, sc, lam, obj, False, eng.counts(), mpn)
+        (si, ss, sl, so), band, counts, mpn = self._gather_merge(3, k, top, band, False, eng.counts(), mpn)
         N, n_viol, n_strong = (int(v) for v in counts)
         k = min(k, N)
         si, sl, so = si[:k], sl[:k], so[:k]
@@ -131,9 +177,11 @@ class ShardedSelector(object):
         if not all_walked and big_m > 0 and pobj < pobj + big_m and mpn - big_m < pobj + big_m:
             # the k strong elements up to the pivot are re-scored obj + big_m and nothing else can reach them
             # (combined_is_strong_prefix in capi.cu): the merged strong list is the answer, no second pass
-            return dict(idx=si, score=so + big_m, lam=sl, obj=so, counts=counts, new_strat=new_strat)
-        idx, sc, lam, obj = eng.topk(4, k, pobj, pidx, 1 if all_walked else 0)
+            return pack((si, so + big_m, sl, so), band, counts, new_strat, 3, (pobj, pidx, False))
+        top = eng.topk(4, k, pobj, pidx, 1 if all_walked else 0)
+        band2 = self._band()
         t = self._t("topk2", t)
-        gi, gs, gl, go, _, _ = self._gather_merge(k, idx, sc, lam, obj, True)
+        top, band2, _, _ = self._gather_merge(4, k, top, band2, True)
+        band2["n_unc_lam"], band2["n_unc_obj"] = band["n_unc_lam"], band["n_unc_obj"]
         self._t("gather+merge2", t)
-        return dict(idx=gi, score=gs, lam=gl, obj=go, counts=counts, new_strat=new_strat)
+        return pack(top, band2, counts, new_strat, 4, (pobj, pidx, bool(all_walked)))
