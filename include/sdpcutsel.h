@@ -189,17 +189,23 @@ int sdpcs_binom(int n, int k, int64_t *out);
 
 /* Eigenvector cuts for m selected subsets (cut_select_qp.py:737-751): sets is m x rho int16 (-1 padded).
  * width = rho + rho(rho+1)/2.  out_ind (m x width, -1 padded): LP columns [x vars | X vars];
- * out_val: coefficients; out_rhs = -v0^2; out_lam: lam_min (eigh); out_violated: lam < thres_neg_eigval. */
+ * out_val: coefficients; out_rhs = -v0^2; out_lam: lam_min (eigh); out_violated: lam < thres_neg_eigval;
+ * out_gap (may be NULL): second smallest eigenvalue minus lam_min -- when it is ~0 the eigenvector (and with it the
+ * cut) is not unique and the reference's row is whatever LAPACK returned; the Python mirror recomputes those rows
+ * with numpy eigh.  vars_values holds n(n+1)/2 + n doubles. */
 int sdpcs_gen_cuts(sdpcs_ctx *ctx, int rho, const int16_t *sets, int64_t m, const double *vars_values,
-                   int64_t *out_ind, double *out_val, double *out_rhs, double *out_lam, uint8_t *out_violated);
+                   int64_t *out_ind, double *out_val, double *out_rhs, double *out_lam, uint8_t *out_violated,
+                   double *out_gap);
 
 /* Row emission in one shot.  The violated cuts of sdpcs_gen_cuts as CSR rows -- row starts
  * out_rowptr[rows+1], LP columns out_ind, coefficients out_val (capacity m x width each), right-hand sides out_rhs[m],
  * sense >= for every row: the arrays CPXaddrows takes, instead of one cplex.SparsePair per cut
- * (cut_select_qp.py:747-754).  out_src[r] (may be NULL) = index into `sets` of row r; *out_nrows = #rows. */
+ * (cut_select_qp.py:747-754).  out_src[r] (may be NULL) = index into `sets` of row r; out_lam / out_gap (may be NULL) =
+ * lam_min and eigenvalue gap of row r; *out_nrows = #rows.  Rows are emitted for lam_min < thres_neg_eigval + guard_lam
+ * (with the default guard a subset within 1e-12 of the threshold is emitted and left to the caller). */
 int sdpcs_gen_cuts_csr(sdpcs_ctx *ctx, int rho, const int16_t *sets, int64_t m, const double *vars_values,
                        int64_t *out_rowptr, int64_t *out_ind, double *out_val, double *out_rhs, int64_t *out_src,
-                       int64_t *out_nrows);
+                       double *out_lam, double *out_gap, int64_t *out_nrows);
 
 /* Triangle-inequality rows (cut_select_qp.py:846-860) for m (triple lex rank, type) pairs as returned by
  * sdpcs_triangles, as CSR: 4 entries per row for types 0..2 (rhs 0), 6 for type 3 (rhs -1), sense >=.

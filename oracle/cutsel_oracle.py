@@ -134,6 +134,17 @@ def cover_all_window(n, rho, r0, r1):
     return out
 
 
+def cover_all_block(n, rho, i1, i2):
+    """The subsets of cover_all(n, rho) whose two leading indices are (i1, i2), in enumeration order (the inner loops of
+    cut_select_qp.py:451-455 for fixed i1 < i2).  int32 (C(n-1-i2, rho-2), rho)."""
+    c = comb(n - 1 - i2, rho - 2)
+    tail = np.fromiter(itertools.chain.from_iterable(itertools.combinations(range(i2 + 1, n), rho - 2)),
+                       dtype=np.int32, count=c * (rho - 2)).reshape(c, rho - 2)
+    out = np.empty((c, rho), dtype=np.int32)
+    out[:, 0], out[:, 1], out[:, 2:] = i1, i2, tail
+    return out
+
+
 def comb(n, k):
     if k < 0 or k > n:
         return 0

@@ -260,30 +260,34 @@ class Engine(object):
                     select_launches=t.select_launches, nn_fallbacks=t.nn_fallbacks, nn_ms=t.nn_ms)
 
     # -- cuts / eig / triangles / nn ---------------------------------------------------------------
-    def gen_cuts(self, rho, sets, vars_values):
+    def gen_cuts(self, rho, sets, vars_values, with_gap=False):
         sets = np.ascontiguousarray(sets, dtype=np.int16).reshape(-1, rho)
         m = sets.shape[0]
         width = rho + rho * (rho + 1) // 2
         ind, val = np.empty((m, width), np.int64), np.empty((m, width))
-        rhs, lam, viol = np.empty(m), np.empty(m), np.empty(m, np.uint8)
+        rhs, lam, viol, gap = np.empty(m), np.empty(m), np.empty(m, np.uint8), np.empty(m)
         v = self._vars(vars_values, required=True)
         self._ck(self._lib.sdpcs_gen_cuts(self._ctx, c_int(rho), _ptr(sets), c_i64(m), _ptr(v), _ptr(ind), _ptr(val), _ptr(rhs),
-                                          _ptr(lam), _ptr(viol)))
+                                          _ptr(lam), _ptr(viol), _ptr(gap)))
+        if with_gap:
+            return ind, val, rhs, lam, viol.astype(bool), gap
         return ind, val, rhs, lam, viol.astype(bool)
 
     def gen_cuts_csr(self, rho, sets, vars_values):
-        """Violated eigenvector cuts as CSR rows: dict(rowptr, ind, val, rhs, src); sense >= for every row."""
+        """Eigenvector cuts as CSR rows: dict(rowptr, ind, val, rhs, src, lam, gap); sense >= for every row.  Rows exist
+        for lam_min < thres_neg_eigval + guard_lam; lam / gap let the caller settle the near-threshold and the
+        non-unique-eigenvector cases with the reference's arithmetic."""
         sets = np.ascontiguousarray(sets, dtype=np.int16).reshape(-1, rho)
         m = sets.shape[0]
         width = rho + rho * (rho + 1) // 2
         rowptr, ind, val = np.zeros(m + 1, np.int64), np.empty(m * width, np.int64), np.empty(m * width)
-        rhs, src, nrows = np.empty(m), np.empty(m, np.int64), c_i64()
+        rhs, src, lam, gap, nrows = np.empty(m), np.empty(m, np.int64), np.empty(m), np.empty(m), c_i64()
         v = self._vars(vars_values, required=True)
         self._ck(self._lib.sdpcs_gen_cuts_csr(self._ctx, c_int(rho), _ptr(sets), c_i64(m), _ptr(v), _ptr(rowptr), _ptr(ind), _ptr(val),
-                                              _ptr(rhs), _ptr(src), ctypes.byref(nrows)))
+                                              _ptr(rhs), _ptr(src), _ptr(lam), _ptr(gap), ctypes.byref(nrows)))
         r = nrows.value
         nnz = int(rowptr[r])
-        return dict(rowptr=rowptr[:r + 1], ind=ind[:nnz], val=val[:nnz], rhs=rhs[:r], src=src[:r])
+        return dict(rowptr=rowptr[:r + 1], ind=ind[:nnz], val=val[:nnz], rhs=rhs[:r], src=src[:r], lam=lam[:r], gap=gap[:r])
 
     def dense_eigcuts(self, vars_values):
         """Strat 0 (cut_select_qp.py:757-786): dict(eigvals (n+1,), ind (width,), val (ncuts, width), rhs (ncuts,))."""

@@ -92,6 +92,7 @@ struct CutArgs {
     const double* X; const double* x;
     double thr_eig; int sweeps;
     i64* ind; double* val; double* rhs; double* lam; uint8_t* violated;   // ind/val: m x width
+    double* gap;           // second smallest eigenvalue minus lam_min: ~0 means the eigenvector is not unique
 };
 
 template <int D>
@@ -117,6 +118,11 @@ __device__ void gen_cut_one(const CutArgs& a, i64 i, const int16_t* s)
 #pragma unroll
     for (int p = 1; p < M; ++p)
         if (A[p][p] < lam) { lam = A[p][p]; best = p; }
+    double second = 1e300;
+#pragma unroll
+    for (int p = 0; p < M; ++p)
+        if (p != best) second = fmin(second, A[p][p]);
+    a.gap[i] = second - lam;
     double v[M];
 #pragma unroll
     for (int p = 0; p < M; ++p) {
@@ -156,7 +162,7 @@ __global__ void __launch_bounds__(128) k_gen_cuts(CutArgs a)
     case 3: gen_cut_one<3>(a, i, s); break;
     case 4: gen_cut_one<4>(a, i, s); break;
     case 5: gen_cut_one<5>(a, i, s); break;
-    default: a.violated[i] = 0; a.lam[i] = 0; a.rhs[i] = 0; break;
+    default: a.violated[i] = 0; a.lam[i] = 0; a.rhs[i] = 0; a.gap[i] = 0; break;
     }
 }
 

@@ -1224,7 +1224,8 @@ extern "C" int sdpcs_merge_topk(sdpcs_ctx* ctx, int64_t m, const double* score, 
 // cuts, eigendecomposition, triangles, NN, peaks
 // ---------------------------------------------------------------------------------------------------
 extern "C" int sdpcs_gen_cuts(sdpcs_ctx* ctx, int rho, const int16_t* sets, int64_t m, const double* vars_values,
-                              int64_t* out_ind, double* out_val, double* out_rhs, double* out_lam, uint8_t* out_violated)
+                              int64_t* out_ind, double* out_val, double* out_rhs, double* out_lam, uint8_t* out_violated,
+                              double* out_gap)
 {
     if (!ctx || m < 0 || rho < 2 || rho > 5) return SDPCS_ERR_INVALID;
     if (!ctx->n) return ctx->fail(SDPCS_ERR_STATE, "set_instance first");
@@ -1237,13 +1238,13 @@ extern "C" int sdpcs_gen_cuts(sdpcs_ctx* ctx, int rho, const int16_t* sets, int6
     if (rc) return rc;
     const int width = rho + rho * (rho + 1) / 2;
     const size_t b_sets = ((size_t)m * rho * 2 + 255) / 256 * 256, b_w = (size_t)m * width * 8, b_m = (size_t)m * 8;
-    if ((rc = ensure_scratch(ctx, b_sets + 2 * b_w + 3 * b_m))) return rc;
+    if ((rc = ensure_scratch(ctx, b_sets + 2 * b_w + 4 * b_m))) return rc;
     char* s = (char*)ctx->d_scratch;
     CutArgs a;
     a.n = ctx->n; a.rho = rho; a.m = m;
     a.sets = (const int16_t*)s;
     a.ind = (i64*)(s + b_sets); a.val = (double*)(s + b_sets + b_w);
-    a.rhs = (double*)(s + b_sets + 2 * b_w); a.lam = a.rhs + m; a.violated = (uint8_t*)(a.lam + m);
+    a.rhs = (double*)(s + b_sets + 2 * b_w); a.lam = a.rhs + m; a.gap = a.lam + m; a.violated = (uint8_t*)(a.gap + m);
     a.X = ctx->d_vars; a.x = ctx->d_vars + (size_t)ctx->n * (ctx->n + 1) / 2;
     a.thr_eig = ctx->params.thres_neg_eigval;
     a.sweeps = ctx->params.jacobi_sweeps > 0 ? ctx->params.jacobi_sweeps : default_sweeps(rho + 1);
@@ -1254,6 +1255,7 @@ extern "C" int sdpcs_gen_cuts(sdpcs_ctx* ctx, int rho, const int16_t* sets, int6
     CU(cudaMemcpyAsync(out_val, a.val, b_w, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(out_rhs, a.rhs, b_m, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(out_lam, a.lam, b_m, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_gap) CU(cudaMemcpyAsync(out_gap, a.gap, b_m, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(out_violated, a.violated, (size_t)m, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return SDPCS_OK;
@@ -1261,10 +1263,11 @@ extern "C" int sdpcs_gen_cuts(sdpcs_ctx* ctx, int rho, const int16_t* sets, int6
 
 // The violated eigenvector cuts of sdpcs_gen_cuts as CSR rows (the layout CPXaddrows takes: row starts, column
 // indices, values, right-hand sides; sense >= for all), in one shot instead of one SparsePair object per cut
-// (cut_select_qp.py:747-754).  out_src[r] = index into `sets` of emitted row r.
+// (cut_select_qp.py:747-754).  out_src[r] = index into `sets` of emitted row r.  With guard_lam > 0 a subset whose lam_min is
+// within the guard of the threshold is emitted too (out_lam tells; the caller decides with the reference's arithmetic).
 extern "C" int sdpcs_gen_cuts_csr(sdpcs_ctx* ctx, int rho, const int16_t* sets, int64_t m, const double* vars_values,
                                   int64_t* out_rowptr, int64_t* out_ind, double* out_val, double* out_rhs, int64_t* out_src,
-                                  int64_t* out_nrows)
+                                  double* out_lam, double* out_gap, int64_t* out_nrows)
 {
     if (!ctx || m < 0 || rho < 2 || rho > 5 || !out_rowptr || !out_nrows) return SDPCS_ERR_INVALID;
     *out_nrows = 0;
@@ -1273,13 +1276,14 @@ extern "C" int sdpcs_gen_cuts_csr(sdpcs_ctx* ctx, int rho, const int16_t* sets, 
     if (!out_ind || !out_val || !out_rhs) return ctx->fail(SDPCS_ERR_INVALID, "null pointer");
     const int width = rho + rho * (rho + 1) / 2;
     std::vector<int64_t> ind((size_t)m * width);
-    std::vector<double> val((size_t)m * width), rhs(m), lam(m);
+    std::vector<double> val((size_t)m * width), rhs(m), lam(m), gap(m);
     std::vector<uint8_t> viol(m);
-    int rc = sdpcs_gen_cuts(ctx, rho, sets, m, vars_values, ind.data(), val.data(), rhs.data(), lam.data(), viol.data());
+    int rc = sdpcs_gen_cuts(ctx, rho, sets, m, vars_values, ind.data(), val.data(), rhs.data(), lam.data(), viol.data(), gap.data());
     if (rc) return rc;
+    const double relaxed = ctx->params.thres_neg_eigval + std::max(ctx->params.guard_lam, 0.0);
     i64 rows = 0, nnz = 0;
     for (i64 i = 0; i < m; ++i) {
-        if (!viol[i]) continue;                                   // eigvals[0] >= _THRES_NEG_EIGVAL: no cut (cut_select_qp.py:743)
+        if (!(lam[i] < relaxed)) continue;                        // eigvals[0] >= _THRES_NEG_EIGVAL: no cut (cut_select_qp.py:743)
         for (int t = 0; t < width; ++t) {
             if (ind[i * width + t] < 0) break;                    // rows of cliques smaller than rho are -1 padded
             out_ind[nnz] = ind[i * width + t];
@@ -1288,6 +1292,8 @@ extern "C" int sdpcs_gen_cuts_csr(sdpcs_ctx* ctx, int rho, const int16_t* sets, 
         }
         out_rhs[rows] = rhs[i];
         if (out_src) out_src[rows] = i;
+        if (out_lam) out_lam[rows] = lam[i];
+        if (out_gap) out_gap[rows] = gap[i];
         out_rowptr[++rows] = nnz;
     }
     *out_nrows = rows;

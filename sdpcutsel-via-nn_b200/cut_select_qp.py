@@ -100,6 +100,11 @@ class B200CutSelection(object):
 
     # -- engines ---------------------------------------------------------------------------------------
     _GUARD_LAM = 10 ** (-12)     # near-tie guard on eigenvalue scores (device vs LAPACK differ by <= ~1e-14)
+    _GAP_TOL = 10 ** (-9)        # eigenvalue gap below which an eigenvector cut is taken from numpy eigh (not unique)
+    # True: every selected cut row (<= 5000 per round) is taken from numpy eigh, i.e. bit-identical to the reference's row.
+    # The device rows agree with those to ~1e-15, but an LP with alternative optima may answer even such a difference
+    # with another vertex; set this when the LP trajectory has to follow the reference's run vertex for vertex.
+    _CUT_ROWS_FROM_LAPACK = False
     _GUARD_OBJ_REL = 4 * 10 ** (-12)   # near-tie guard on optimality measures, times rho * max|Q_arr| (the scale of max_elem)
 
     def _guards(self):
@@ -213,17 +218,42 @@ class B200CutSelection(object):
         out.n_violated = int(res["counts"][1])
         out.degenerate, out.n_near_ties = int(res["degenerate"]), int(res["n_near_ties"])
         X_vals, x_vals = vars_values[:nb_lifted], vars_values[nb_lifted:]
-        sets = self._sets_of(agg, res["idx"])
+        # the reference's tuples, built column-wise (numpy gathers + tolist) instead of entry by entry
+        sets, xinds, sizes, pts, Xs = self._entry_columns(agg, res["idx"], x_vals, X_vals, with_values=(strat_eff != 1))
         if strat_eff == 1:
-            for s, sc in zip(sets, res["score"]):
-                out.append((s, float(sc), cover.xarr_inds(n, s), len(s)))      # cut_select_qp.py:649
+            out.extend(zip(sets, res["score"].tolist(), xinds, sizes))                # cut_select_qp.py:649
             return out
-        for i, s, sc in zip(res["idx"], sets, res["score"]):
-            xi = cover.xarr_inds(n, s)
-            out.append((int(i), float(sc), tuple(x_vals[s]), tuple(X_vals[xi])))  # cut_select_qp.py:599
+        out.extend(zip(res["idx"].tolist(), res["score"].tolist(), pts, Xs))          # cut_select_qp.py:599
         if strat_eff == 4:
             return (int(res["new_strat"]), out)                                    # cut_select_qp.py:629-630
         return out
+
+    def _entry_columns(self, agg, idx, x_vals, X_vals, with_values):
+        """Per selected candidate: set_inds list, Xarr_inds list (cut_select_qp.py:530-531), size, and -- for the optimality
+        formats -- curr_pt / X_slice tuples (:573-574).  Grouped by subset size so that everything is array work."""
+        rows = self._set_rows(agg, idx)
+        m, n = rows.shape[0], self._nb_vars
+        sets, xinds, pts, Xs = [None] * m, [None] * m, [None] * m, [None] * m
+        sizes = (rows >= 0).sum(axis=1)
+        for d in np.unique(sizes):
+            where = np.nonzero(sizes == d)[0]
+            sub = rows[where, :d]
+            pt = neartie._pairs(int(d))
+            a, b = sub[:, pt[:, 0]], sub[:, pt[:, 1]]
+            xi = n * a - a * (a + 1) // 2 + b
+            cols = [sub.tolist(), xi.tolist()]
+            if with_values:
+                cols += [list(map(tuple, x_vals[sub].tolist())), list(map(tuple, X_vals[xi].tolist()))]
+            if where.size == m:
+                sets, xinds = cols[0], cols[1]
+                if with_values:
+                    pts, Xs = cols[2], cols[3]
+            else:
+                for j, p in enumerate(where.tolist()):
+                    sets[p], xinds[p] = cols[0][j], cols[1][j]
+                    if with_values:
+                        pts[p], Xs[p] = cols[2][j], cols[3][j]
+        return sets, xinds, sizes.tolist(), pts, Xs
 
     def _select_resolved(self, eng, agg, strat, vars_values, k):
         """Device selection (winners + guard band) followed by the near-tie resolution of neartie.resolve.  If re-scoring
@@ -301,7 +331,16 @@ class B200CutSelection(object):
                 packed[i, :len(s)] = s
         coeffs_sdp, rhs_sdp, senses_sdp = [], [], []
         if packed is not None and packed.shape[0]:
-            csr = self._any_engine().gen_cuts_csr(packed.shape[1], packed, vars_values)   # violated cuts only (eigvals[0] < _THRES_NEG_EIGVAL)
+            eng = self._any_engine()
+            csr = eng.gen_cuts_csr(packed.shape[1], packed, vars_values)   # violated cuts only (eigvals[0] < _THRES_NEG_EIGVAL)
+            # rows whose eigenvector is not unique (repeated smallest eigenvalue: every LP vertex has them) or whose lam_min
+            # is within the guard of the threshold: the reference's row is what numpy eigh returns -- recompute those
+            thr = float(self._THRES_NEG_EIGVAL)
+            fix = (csr["gap"] <= self._GAP_TOL) | (np.abs(csr["lam"] - thr) <= float(eng.params.guard_lam))
+            if self._CUT_ROWS_FROM_LAPACK:
+                fix[:] = True
+            if fix.any():
+                csr = neartie.fix_cut_rows(csr, packed, fix, self._nb_vars, vars_values, thr)
             if _add_rows_csr(my_prob, csr):
                 return len(csr["rhs"])
             coeffs_sdp, rhs_sdp = _sparse_pairs(csr), csr["rhs"].tolist()
@@ -321,6 +360,15 @@ class B200CutSelection(object):
         if eng is None or eng.n != self._nb_vars or getattr(self, "_dense_engine_Q", None) is not self._Q_arr:
             self._dense_engine, self._dense_engine_Q = self._new_engine(), self._Q_arr
         d = self._dense_engine.dense_eigcuts(vars_values)
+        # a repeated negative eigenvalue (LP vertices have them) leaves the individual eigenvectors -- hence the rows --
+        # undetermined: take them from numpy eigh like the reference does; likewise an eigenvalue within the guard of the
+        # threshold, or when rows bit-identical to the reference's are asked for
+        ev, thr = d["eigvals"], float(self._THRES_NEG_EIGVAL)
+        m_neg = int((ev[:self._nb_vars] < thr + self._GUARD_LAM).sum())
+        near = m_neg and (np.diff(ev[:min(m_neg + 1, ev.size)]) <= self._GAP_TOL).any()
+        if self._CUT_ROWS_FROM_LAPACK or near or (np.abs(ev - thr) <= self._GUARD_LAM).any():
+            val, rhs, _ = neartie.lapack_dense_rows(self._nb_vars, np.asarray(vars_values, dtype=np.float64), thr)
+            d = dict(d, val=val, rhs=rhs)
         nb, width = d["val"].shape
         csr = dict(rowptr=np.arange(nb + 1, dtype=np.int64) * width, ind=np.tile(d["ind"], nb), val=d["val"].ravel(), rhs=d["rhs"])
         if not _add_rows_csr(self._my_prob, csr):
@@ -350,7 +398,7 @@ class B200CutSelection(object):
         csr = _capi.triangle_rows_csr(n, t["rank"][:nb_tri_cuts], t["type"][:nb_tri_cuts])      # cut_select_qp.py:846-860
         if _add_rows_csr(my_prob, csr):
             return nb_tri_cuts
-        coeffs_tri, rhs_tri = _sparse_pairs(csr, as_int=True), [int(v) for v in csr["rhs"]]
+        coeffs_tri, rhs_tri = _sparse_pairs(csr, as_int=True), csr["rhs"].astype(np.int64).tolist()
         senses_tri = ["G"] * nb_tri_cuts
         my_prob.linear_constraints.add(lin_expr=coeffs_tri, rhs=rhs_tri, senses=senses_tri)
         return nb_tri_cuts
@@ -369,7 +417,7 @@ def _add_rows_csr(my_prob, csr):
 def _sparse_pairs(csr, as_int=False):
     """CSR -> the reference's list of cplex.SparsePair (cut_select_qp.py:747, 849-858), sliced from two flat lists."""
     ind, ptr = csr["ind"].tolist(), csr["rowptr"].tolist()
-    val = [int(v) for v in csr["val"]] if as_int else csr["val"].tolist()
+    val = csr["val"].astype(np.int64).tolist() if as_int else csr["val"].tolist()
     return [SparsePair(ind=ind[a:b], val=val[a:b]) for a, b in zip(ptr[:-1], ptr[1:])]
 
 

@@ -227,3 +227,77 @@ def resolve(res, k, rescorer, guard_lam, guard_obj):
     unresolved = open_band or (strat == 4 and path == 4 and (unc_elsewhere or unc_l.any() or unc_o.any()))
     out["degenerate"] = 2 if unresolved else 1
     return out
+
+
+def lapack_cut_rows(x_s, X_s, thr_eig):
+    """Eigenvector cuts of cut_select_qp.py:737-751 in the reference's arithmetic, batched over subsets of one size d:
+    w, V = eigh(M, 'U'); v = V[:, 0] with |v_i| <= 1e-15 zeroed; row = [2 v0 v_i | v_i v_j (x 2 if i != j)], rhs = -v0^2.
+    Returns (val (m, d + d(d+1)/2), rhs (m,), lam_min (m,), violated (m,))."""
+    x_s = np.asarray(x_s, dtype=np.float64)
+    m, d = x_s.shape
+    M = np.zeros((m, d + 1, d + 1))
+    M[:, 0, 0] = 1.0
+    M[:, 0, 1:] = x_s
+    iu = np.triu_indices(d)
+    M[:, 1 + iu[0], 1 + iu[1]] = X_s
+    w, V = np.linalg.eigh(M, "U")
+    v = V[:, :, 0]
+    v = np.where(np.abs(v) <= -thr_eig, 0, v)
+    i1 = np.array([a for a in range(d + 1) for b in range(max(a, 1), d + 1)])
+    i2 = np.array([b for a in range(d + 1) for b in range(max(a, 1), d + 1)])
+    val = v[:, i1] * v[:, i2] * np.where(i1 != i2, 2.0, 1.0)[None, :]
+    return val, -v[:, 0] * v[:, 0], w[:, 0], w[:, 0] < thr_eig
+
+
+def fix_cut_rows(csr, sets, fix, n, vars_values, thr_eig):
+    """Replace the CSR rows flagged in `fix` (eigenvector not unique: eigenvalue gap ~ 0, or lam_min inside the guard of the
+    violation threshold) by the rows the reference's numpy eigh produces; rows eigh does not find violated are dropped.
+    sets: (m, rho) int array (-1 padded) indexed by csr['src']."""
+    fix = np.asarray(fix, dtype=bool)
+    v = np.asarray(vars_values, dtype=np.float64)
+    nl = n * (n + 1) // 2
+    X_vals, x_vals = v[:nl], v[nl:]
+    rows = np.nonzero(fix)[0]
+    sub = np.asarray(sets, dtype=np.int64)[csr["src"][rows]]
+    sizes = (sub >= 0).sum(axis=1)
+    val, rhs, lam = csr["val"].copy(), csr["rhs"].copy(), csr["lam"].copy()
+    keep = np.ones(csr["rhs"].shape[0], dtype=bool)
+    for d in np.unique(sizes):
+        sel = np.nonzero(sizes == d)[0]
+        s = sub[sel, :d]
+        pt = _pairs(int(d))
+        a, b = s[:, pt[:, 0]], s[:, pt[:, 1]]
+        xinds = n * a - a * (a + 1) // 2 + b
+        nv, nr, w0, viol = lapack_cut_rows(x_vals[s], X_vals[xinds], thr_eig)
+        r = rows[sel]
+        val[csr["rowptr"][r][:, None] + np.arange(nv.shape[1])[None, :]] = nv
+        rhs[r], lam[r], keep[r] = nr, w0, viol
+    out = dict(csr, val=val, rhs=rhs, lam=lam)
+    if keep.all():
+        return out
+    lens = np.diff(csr["rowptr"])
+    mask = np.repeat(keep, lens)
+    out.update(rowptr=np.concatenate([[0], np.cumsum(lens[keep])]).astype(np.int64), ind=csr["ind"][mask], val=val[mask],
+               rhs=rhs[keep], lam=lam[keep], src=csr["src"][keep], gap=csr["gap"][keep])
+    return out
+
+
+def lapack_dense_rows(n, vars_values, thr_eig):
+    """Dense eigenvalue cuts (strat 0) in the reference's arithmetic (cut_select_qp.py:757-786): one eigh of the full
+    [1 x^T; x X]; every eigenvalue among the n smallest below the threshold gives the row
+    [2 v0 v_i | v_i v_j (x 2 if i != j)] >= -v0^2.  Returns (val (ncuts, n + n(n+1)/2), rhs (ncuts,), eigvals)."""
+    v = np.asarray(vars_values, dtype=np.float64)
+    nl = n * (n + 1) // 2
+    mat = np.zeros((n + 1, n + 1))
+    mat[0, 0] = 1
+    mat[0, 1:] = v[nl:]
+    iu = np.triu_indices(n)
+    mat[iu[0] + 1, iu[1] + 1] = v[:nl]
+    w, V = np.linalg.eigh(mat, "U")
+    i1, i2 = np.triu_indices(n + 1)
+    keep = i2 >= 1
+    i1, i2 = i1[keep], i2[keep]
+    cols = [ix for ix in range(n) if w[ix] < thr_eig]
+    vals = np.array([V[i1, ix] * V[i2, ix] * np.where(i1 != i2, 2.0, 1.0) for ix in cols]).reshape(len(cols), n + nl)
+    rhs = np.array([-V[0, ix] * V[0, ix] for ix in cols])
+    return vals, rhs, w

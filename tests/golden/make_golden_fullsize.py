@@ -13,7 +13,6 @@ the GPU selection with these lists (bench.py prints `selection.matches_oracle_go
 Candidates are enumerated per (i1, i2) prefix with itertools.combinations -- the order of the reference's nested loops
 (cut_select_qp.py:451-455) -- so that no unranking code of the product is involved.
 """
-import itertools
 import multiprocessing as mp
 import os
 import sys
@@ -59,10 +58,7 @@ def job(args):
     obj_m = np.memmap(os.path.join(SHM, "sdpcs_gold_obj.f64"), dtype=np.float64, mode="r+", shape=(N,))
     done = 0
     for i1, i2, r0, c in batch:
-        tail = np.fromiter(itertools.chain.from_iterable(itertools.combinations(range(i2 + 1, n), rho - 2)),
-                           dtype=np.int32, count=c * (rho - 2)).reshape(c, rho - 2)
-        idx = np.empty((c, rho), dtype=np.int32)
-        idx[:, 0], idx[:, 1], idx[:, 2:] = i1, i2, tail
+        idx = orc.cover_all_block(n, rho, i1, i2)
         lam, obj = orc.score_cover(Q_arr, n, idx, np.full(c, rho), vv, blobs)
         lam_m[r0:r0 + c], obj_m[r0:r0 + c] = lam, obj
         done += c

@@ -106,6 +106,88 @@ def test_whole_cover_selection_properties(capi, blobs, inst, rho):
     assert np.abs(-lam_o - r1["score"]).max() < LAM_TOL
 
 
+@pytest.fixture(scope="module")
+def fullsize_golden():
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fullsize_topk.npz")
+    with np.load(path) as z:
+        return {k: z[k] for k in z.files}
+
+
+@pytest.mark.parametrize("rho", [4, 5])
+def test_whole_cover_selection_equals_the_oracles(capi, blobs, inst, fullsize_golden, rho):
+    """BASELINE configs[2] / configs[3] at full size: the first 5000 entries of strat 1, 2 and 4 are the ORACLE's own lists,
+    index for index (tests/golden/fullsize_topk.npz: the oracle scored all 9,691,375 / 234,531,275 subsets with LAPACK +
+    the NNs.so-exact network, tests/golden/make_golden_fullsize.py), through the raw C ABI and through the guarded,
+    near-tie-resolved selection of the drop-in."""
+    import sdpcutsel_via_nn_b200 as pkg
+    from sdpcutsel_via_nn_b200 import neartie
+    from sdpcutsel_via_nn_b200.distributed import ShardedSelector
+    n, Q_arr, vv = inst
+    g, tag, k = fullsize_golden, "n%d_rho%d" % (n, rho), 5000
+    eng = _engine(capi, blobs, n, Q_arr, rho)
+    eng.set_cover_all(rho)
+    rescorer = neartie.Rescorer(n, Q_arr, vv, blobs, lambda i: capi.unrank(n, rho, i))
+    sel = ShardedSelector(eng, local=True)
+    for strat, tol in ((1, LAM_TOL), (2, OBJ_TOL), (4, OBJ_TOL)):
+        r = eng.select(strat, vv if strat == 1 else None, k)
+        assert np.array_equal(r["idx"], g["%s_s%d_idx" % (tag, strat)])
+        assert np.abs(r["score"] - g["%s_s%d_score" % (tag, strat)]).max() < tol
+        res = neartie.resolve(sel.select(strat, None, k), k, rescorer, float(eng.params.guard_lam), float(eng.params.guard_obj))
+        assert np.array_equal(res["idx"], g["%s_s%d_idx" % (tag, strat)]) and res["degenerate"] == 0 and res["n_near_ties"] == 0
+    assert r["new_strat"] == int(g[tag + "_s4_newstrat"]) and [int(v) for v in r["counts"]] == g[tag + "_s4_counts"].tolist()
+    eng.score(None, 3)
+    eng.topk(3, k)
+    assert [int(v) for v in eng.counts()] == [capi.binom(n, rho), int(g[tag + "_n_violated"]), int(g[tag + "_n_strong"])]
+
+
+def _nccl_worker(rank, world, port, ret):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import sdpcutsel_via_nn_b200 as pkg
+    n, rho, k = 125, 4, 5000
+    Q_arr, _ = orc.boxqp_arrays(orc.synth_instance(n, 0.75, seed=7))
+    vv = orc.synth_point(n, seed=8)
+    eng = pkg._capi.Engine(rank)
+    eng.set_weights(rho, pkg.nn_weights.load_packed(rho))
+    eng.set_instance(n, Q_arr)
+    N = pkg._capi.binom(n, rho)
+    r0, r1 = pkg.distributed.shard_range(N, world, rank)
+    eng.set_cover_all(rho, r0, r1)
+    sel = pkg.distributed.ShardedSelector(eng, device=torch.device("cuda", rank))
+    out = {}
+    for strat in (1, 2, 4):
+        r = sel.select(strat, vv, k)
+        out[strat] = (r["idx"].tolist(), int(r["new_strat"]), [int(v) for v in r["counts"]], r["guard"])
+    ret[rank] = out
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_selection_on_real_engines_under_nccl(fullsize_golden):
+    """Two ranks, two GPUs, NCCL: ShardedSelector on real engines returns the oracle's whole-cover lists on every rank."""
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ret = mp.Manager().dict()
+    mp.spawn(_nccl_worker, args=(2, port, ret), nprocs=2, join=True)
+    g = fullsize_golden
+    assert ret[0][1][0] == ret[1][1][0] and ret[0][4] == ret[1][4]
+    for strat in (1, 2, 4):
+        assert ret[0][strat][0] == g["n125_rho4_s%d_idx" % strat].tolist()
+    assert ret[0][4][1] == int(g["n125_rho4_s4_newstrat"]) and ret[0][4][2] == g["n125_rho4_s4_counts"].tolist()
+
+
 def test_n250_ranks_beyond_32_bits(capi, blobs):
     """n = 250 (the largest instances of the reference), rho = 5: C(250,5) = 7,817,031,300 > 2^32; windows at the far end
     and in the middle of the rank space against the oracle (64-bit unranking, gathers over the 251 KB instance arrays)."""

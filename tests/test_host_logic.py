@@ -89,3 +89,28 @@ def test_triangle_rows_csr_match_the_reference_rows():
         pkg._capi.triangle_rows_csr(n, [T], [0])
     with pytest.raises(pkg._capi.SdpcsError):
         pkg._capi.triangle_rows_csr(n, [0], [4])
+
+
+def test_mixin_composition_with_the_reference_classes():
+    """make_solvers in front of the unmodified reference (no device needed to check the wiring): the hot-path methods
+    resolve to the GPU ones, the name-mangled private methods are overridden under the reference's class names, the
+    QCQP class keeps the reference's cut_select_algo but not its O(N^2) cover algebra, and the 4e6 wall is lifted on the
+    class cut_select_algo reads it from (cut_select_qp.py:117)."""
+    import refloader
+    loaded = refloader.load_reference()
+    if loaded is None:
+        pytest.skip("no reference tree")
+    ref, refq, _ = loaded
+    G, GQ = pkg.make_solvers(ref, refq)
+    B = pkg.B200CutSelection
+    for name in ("_load_neural_nets", "_get_sdp_vertex_cover", "_sel_eigcut_by_ordering_on_measure", "_gen_eigcuts_selected",
+                 "_get_eigendecomp"):
+        assert getattr(G, name) is getattr(B, name) and getattr(GQ, name) is getattr(B, name)
+    assert G.cut_select_algo is ref.CutSolver.cut_select_algo and GQ.cut_select_algo is refq.CutSolverQCQP.cut_select_algo
+    for name in ("_CutSolver__preprocess_triangle_ineq", "_CutSolver__separate_and_add_triangle", "_CutSolver__gen_dense_eigcuts"):
+        assert name in G.__dict__
+    assert "_CutSolverQCQP__get_vertex_cover" in GQ.__dict__
+    assert [c.__name__ for c in GQ.__mro__[:5]] == ["CutSolverQCQP", "CutSolverQCQP", "_Mix", "B200CutSelection", "CutSolver"]
+    assert ref.CutSolver._THRES_MAX_SUBS == B._THRES_MAX_SUBS == 2 ** 44
+    g = G()
+    assert g._Mat[0].shape == (3, 3) and g._blobs == {}          # both __init__ ran
