@@ -246,7 +246,19 @@ def golden_check(wl, strat, idx):
 
 def dropin_rounds(name, reps=3):
     """Separation rounds of a real instance through the drop-in CutSolver surface (what cut_select_algo calls per round,
-    cut_select_qp.py:162-187): selection, cut rows, triangle rows.  Wall clock, host buffers, LP sink included."""
+    cut_select_qp.py:162-187): selection, cut rows, triangle rows.  Wall clock, host buffers, LP sink included.
+    The cyclic garbage collector is paused while rounds are timed: a round allocates ~50,000 small Python objects (the
+    reference's tuple / SparsePair formats) and a generation-2 collection landing inside one costs more than the round."""
+    import gc
+    gc.collect()
+    gc.disable()
+    try:
+        return _dropin_rounds(name, reps)
+    finally:
+        gc.enable()
+
+
+def _dropin_rounds(name, reps):
     import sdpcutsel_via_nn_b200 as pkg
     from oracle import cutsel_oracle as orc
     g = np.load(os.path.join(ROOT, "tests", "golden", "reference_golden.npz"))
