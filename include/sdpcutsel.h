@@ -175,6 +175,22 @@ int sdpcs_last_band(sdpcs_ctx *ctx, int64_t cap, int64_t *out_idx, double *out_s
 int sdpcs_merge_topk(sdpcs_ctx *ctx, int64_t m, const double *score, const double *obj2, const int64_t *idx,
                      int64_t k, int64_t *out_perm, int64_t *out_n);
 
+/* Multi-GPU exchange without a host hop.  sdpcs_topk_pack_dev = sdpcs_topk whose result stays on the device,
+ * packed into the caller's DEVICE buffer d_block of (2 + k + band_rows) x 4 doubles: two header rows
+ * [len, N_local, #violated, #strong], [max positive non-violated obj, n_unc_lam, n_unc_obj, band open] and the local
+ * winners followed by up to band_rows near ties as rows [agg_idx, score, lam, obj].  The ranks all-gather their blocks
+ * (ncclAllGather / torch.distributed on the context's stream: 16 (k + band_rows + 2) B per rank), then
+ * sdpcs_merge_packed_dev merges the `world` gathered blocks on the device with the selection comparator
+ * (score desc, obj desc if use_obj2, agg_idx asc) and downloads only the global winners (*out_n <= k) followed by
+ * their guard band (*out_band rows within delta of the k-th score); out_* have capacity out_cap.
+ * out_hdr[8] = {rows merged, sum N, sum #violated, sum #strong, max of the extras, sum n_unc_lam, sum n_unc_obj,
+ * band open}. */
+int sdpcs_topk_pack_dev(sdpcs_ctx *ctx, int mode, int64_t k, double pivot_obj, int64_t pivot_idx, int all_walked,
+                        int64_t band_rows, void *d_block);
+int sdpcs_merge_packed_dev(sdpcs_ctx *ctx, const void *d_gathered, int world, int64_t rows_cap, int64_t k, int use_obj2,
+                           double delta, int64_t out_cap, int64_t *out_idx, double *out_score, double *out_lam,
+                           double *out_obj, int64_t *out_n, int64_t *out_band, double *out_hdr);
+
 /* One-call selection on a single GPU with HOST buffers (upload + score + select + download):
  * the whole of _sel_eigcut_by_ordering_on_measure (cut_select_qp.py:543-654) for strat 1, 2, 4, returning the
  * prefix of length <= k of the ranked list.  out_counts = {N, #violated walked, #strong}; out_new_strat as

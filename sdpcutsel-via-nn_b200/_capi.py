@@ -21,7 +21,7 @@ EXPORTS = [
     "sdpcs_select", "sdpcs_unrank", "sdpcs_binom", "sdpcs_gen_cuts", "sdpcs_eigendecomp", "sdpcs_set_tri_pattern",
     "sdpcs_triangles", "sdpcs_nn_eval", "sdpcs_nn_debug_layer", "sdpcs_fp64_peak",
     "sdpcs_set_cover_pattern", "sdpcs_get_cover_rows", "sdpcs_cover_restrict", "sdpcs_gen_cuts_csr", "sdpcs_triangle_rows_csr", "sdpcs_dense_eigcuts", "sdpcs_max_pos_nonviolated",
-    "sdpcs_last_band",
+    "sdpcs_last_band", "sdpcs_topk_pack_dev", "sdpcs_merge_packed_dev",
 ]
 
 NN_TCGEN05, NN_DMMA = 0, 1
@@ -225,6 +225,22 @@ class Engine(object):
             m = n.value
         return dict(idx=idx[:m], score=sc[:m], lam=lam[:m], obj=obj[:m], n_band=int(info[0]), band_open=int(info[1]),
                     n_unc_lam=int(info[2]), n_unc_obj=int(info[3]))
+
+    def topk_pack_dev(self, mode, k, band_rows, block_ptr, pivot_obj=0.0, pivot_idx=0, all_walked=0):
+        """sdpcs_topk whose result stays on the device, packed into the DEVICE buffer at block_ptr ((2 + k + band_rows) x 4 f64)."""
+        self._ck(self._lib.sdpcs_topk_pack_dev(self._ctx, c_int(mode), c_i64(int(k)), c_dbl(pivot_obj), c_i64(int(pivot_idx)),
+                                               c_int(all_walked), c_i64(int(band_rows)), c_vp(block_ptr)))
+
+    def merge_packed_dev(self, gathered_ptr, world, rows_cap, k, use_obj2, delta, out_cap):
+        """Merge `world` gathered blocks on the device; returns (idx, score, lam, obj, n_winners, n_band, hdr[8])."""
+        cap = max(int(out_cap), 1)
+        idx, sc, lam, obj = np.empty(cap, np.int64), np.empty(cap), np.empty(cap), np.empty(cap)
+        n, nb, hdr = c_i64(), c_i64(), np.zeros(8)
+        self._ck(self._lib.sdpcs_merge_packed_dev(self._ctx, c_vp(gathered_ptr), c_int(world), c_i64(int(rows_cap)), c_i64(int(k)),
+                                                  c_int(1 if use_obj2 else 0), c_dbl(delta), c_i64(int(out_cap)), _ptr(idx), _ptr(sc),
+                                                  _ptr(lam), _ptr(obj), ctypes.byref(n), ctypes.byref(nb), _ptr(hdr)))
+        m = n.value + nb.value
+        return idx[:m], sc[:m], lam[:m], obj[:m], n.value, nb.value, hdr
 
     def max_pos_nonviolated(self):
         out = c_dbl()

@@ -14,6 +14,7 @@
 #include "score_kernels.cuh"
 #include "mlp_i8_kernels.cuh"
 #include "select_kernels.cuh"
+#include "exchange_kernels.cuh"
 
 using namespace sdpcs;
 
@@ -1063,6 +1064,75 @@ extern "C" int sdpcs_counts(sdpcs_ctx* ctx, int64_t* out3)
 {
     if (!ctx || !out3) return SDPCS_ERR_INVALID;
     out3[0] = ctx->last_counts[0]; out3[1] = ctx->last_counts[1]; out3[2] = ctx->last_counts[2];
+    return SDPCS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// multi-GPU exchange on the device (exchange_kernels.cuh)
+// ---------------------------------------------------------------------------------------------------
+extern "C" int sdpcs_topk_pack_dev(sdpcs_ctx* ctx, int mode, int64_t k, double pivot_obj, int64_t pivot_idx, int all_walked,
+                                   int64_t band_rows, void* d_block)
+{
+    if (!ctx || !d_block || k < 0 || band_rows < 0) return SDPCS_ERR_INVALID;
+    if (!ctx->mode) return ctx->fail(SDPCS_ERR_STATE, "cover not set");
+    CU(cudaSetDevice(ctx->device));
+    int rc = topk_device(ctx, mode, k, pivot_obj, pivot_idx, all_walked);
+    if (rc) return rc;
+    const SelState* st = ctx->h_state;
+    const i64 rows_cap = k + band_rows;
+    const i64 band = std::max<i64>(std::min<i64>(st->band_count, ctx->sel_cap - st->k_out), 0);
+    const i64 rows = std::min<i64>(st->k_out + band, rows_cap);
+    PackHdr h;
+    h.len = (double)rows; h.n_local = (double)ctx->N; h.n_violated = (double)st->n_violated; h.n_strong = (double)st->n_strong;
+    h.extra = st->max_pos_nonviol ? dec_key(st->max_pos_nonviol) : -INFINITY;
+    h.n_unc_lam = (double)st->n_unc_lam; h.n_unc_obj = (double)st->n_unc_obj;
+    h.open = (st->band_open || st->k_out + band > rows_cap) ? 1.0 : 0.0;
+    ctx->last_counts[0] = ctx->N; ctx->last_counts[1] = st->n_violated; ctx->last_counts[2] = st->n_strong;
+    ctx->last_max_pos_nonviol = h.extra;
+    k_pack_rows<<<(unsigned)std::max<i64>(1, (rows_cap + 255) / 256), 256, 0, ctx->stream>>>(h, rows, rows_cap, ctx->d_s_idx, ctx->d_o_score,
+                                                                                              ctx->d_o_lam, ctx->d_o_obj, (double*)d_block);
+    CU(cudaGetLastError());
+    ctx->tm.select_launches++;
+    return SDPCS_OK;
+}
+
+extern "C" int sdpcs_merge_packed_dev(sdpcs_ctx* ctx, const void* d_gathered, int world, int64_t rows_cap, int64_t k, int use_obj2,
+                                      double delta, int64_t out_cap, int64_t* out_idx, double* out_score, double* out_lam,
+                                      double* out_obj, int64_t* out_n, int64_t* out_band, double* out_hdr)
+{
+    if (!ctx || !d_gathered || world < 1 || rows_cap < 0 || k < 0 || out_cap < 0 || !out_n || !out_band || !out_hdr) return SDPCS_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)(16 + 4 * std::max<i64>(out_cap, 1)) * 8;
+    int rc = ensure_scratch(ctx, bytes);
+    if (rc) return rc;
+    if ((rc = ensure_hout(ctx, bytes))) return rc;
+    double* d_out = (double*)ctx->d_scratch;
+    const i64 threads = (i64)world * rows_cap;
+    if (threads > 0)
+        k_merge_rows<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>((const double*)d_gathered, world, rows_cap, use_obj2, out_cap, d_out);
+    k_merge_finish<<<1, 32, 0, ctx->stream>>>((const double*)d_gathered, world, rows_cap, k, delta, out_cap, d_out);
+    CU(cudaGetLastError());
+    // header first (it says how many rows are worth copying): one small copy, then the rows
+    double* h = (double*)ctx->h_out;
+    CU(cudaMemcpyAsync(h, d_out, 16 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    const i64 guess = std::min<i64>(out_cap, k + 64);
+    if (guess > 0) CU(cudaMemcpyAsync(h + 16, d_out + 16, (size_t)guess * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const i64 nwin = (i64)h[8], nband = (i64)h[9], tot = nwin + nband;
+    if (tot > guess) {
+        CU(cudaMemcpyAsync(h + 16 + 4 * guess, d_out + 16 + 4 * guess, (size_t)(tot - guess) * 32, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    for (i64 i = 0; i < tot; ++i) {
+        const double* r = h + 16 + 4 * i;
+        if (out_idx) out_idx[i] = (int64_t)r[0];
+        if (out_score) out_score[i] = r[1];
+        if (out_lam) out_lam[i] = r[2];
+        if (out_obj) out_obj[i] = r[3];
+    }
+    *out_n = nwin; *out_band = nband;
+    for (int j = 0; j < 8; ++j) out_hdr[j] = h[j];
+    ctx->tm.select_launches += 2;
     return SDPCS_OK;
 }
 

@@ -48,6 +48,11 @@ class ShardedSelector(object):
                 self.dist = None
         self.world = self.dist.get_world_size(group) if self.dist else 1
         self.prof = {} if os.environ.get("SDPCS_DIST_PROFILE") else None     # phase -> accumulated seconds (host clock)
+        # device-resident exchange: pack on the GPU, NCCL all-gather of device buffers, merge on the GPU (no host hop);
+        # engines without the entry points (CPU stand-ins in the gloo tests) use the host-staged exchange below
+        self.dev_exchange = (self.world > 1 and device is not None and getattr(device, "type", "cuda") == "cuda"
+                             and hasattr(engine, "topk_pack_dev") and not os.environ.get("SDPCS_HOST_EXCHANGE"))
+        self._bufs = {}
 
     def _t(self, name, t0):
         if self.prof is not None:
@@ -66,6 +71,31 @@ class ShardedSelector(object):
         out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
         self.dist.all_gather_into_tensor(out, t, group=self.group)
         return out.cpu().numpy().reshape((self.world,) + tuple(t.shape))
+
+    def _topk_exchange(self, mode, k, pivot=(0.0, 0, 0), want_counts=True):
+        """Local top-k of `mode` + exchange + merge.  Returns (winners (idx, score, lam, obj), band dict, summed counters,
+        max over ranks of the largest positive non-violated obj)."""
+        eng = self.eng
+        if not self.dev_exchange:
+            top = eng.topk(mode, k, *pivot)
+            band = self._band()
+            mpn = eng.max_pos_nonviolated() if (mode == 3 and hasattr(eng, "max_pos_nonviolated")) else (np.inf if mode == 3 else 0.0)
+            return self._gather_merge(mode, k, top, band, mode == 4, eng.counts() if want_counts else None, mpn)
+        import torch
+        rows_cap = k + BAND_ROWS
+        if rows_cap not in self._bufs:
+            self._bufs = {rows_cap: (torch.empty((2 + rows_cap) * 4, dtype=torch.float64, device=self.device),
+                                     torch.empty(self.world * (2 + rows_cap) * 4, dtype=torch.float64, device=self.device))}
+        send, recv = self._bufs[rows_cap]
+        eng.set_stream(torch.cuda.current_stream(self.device).cuda_stream)      # the collective is ordered on this stream
+        eng.topk_pack_dev(mode, k, BAND_ROWS, send.data_ptr(), *pivot)
+        self.dist.all_gather_into_tensor(recv, send, group=self.group)
+        idx, sc, lam, obj, nwin, nband, hdr = eng.merge_packed_dev(recv.data_ptr(), self.world, rows_cap, k, mode == 4,
+                                                                   self._guard_of(mode), k + self.world * BAND_ROWS)
+        band = dict(idx=idx[nwin:], score=sc[nwin:], lam=lam[nwin:], obj=obj[nwin:], n_band=int(nband), band_open=int(hdr[7]),
+                    n_unc_lam=int(hdr[5]), n_unc_obj=int(hdr[6]))
+        counts = np.array([int(hdr[1]), int(hdr[2]), int(hdr[3])], dtype=np.int64) if want_counts else None
+        return (idx[:nwin], sc[:nwin], lam[:nwin], obj[:nwin]), band, counts, float(hdr[4])
 
     def _band(self):
         """Guard band + counters of the engine's last top-k pass (engines without a guard report none)."""
@@ -149,22 +179,15 @@ class ShardedSelector(object):
                         band={key: band[key] for key in ("idx", "score", "lam", "obj")}, guard=guard)
 
         if strat != 4:
-            top = eng.topk(strat, k)
-            band = self._band()
-            t = self._t("score+topk", t)
-            top, band, counts, _ = self._gather_merge(strat, k, top, band, False, eng.counts())
-            self._t("exchange+merge", t)
+            top, band, counts, _ = self._topk_exchange(strat, k)
+            self._t("topk+exchange+merge", t)
             return pack(top, band, counts, strat, strat)
-        top = eng.topk(3, k)
-        band = self._band()
-        t = self._t("score+topk1", t)
         # the pivot of the combined rule needs k <= N; N is only known after the exchange, so gather k rows and cut after
-        mpn = eng.max_pos_nonviolated() if hasattr(eng, "max_pos_nonviolated") else np.inf
-        (si, ss, sl, so), band, counts, mpn = self._gather_merge(3, k, top, band, False, eng.counts(), mpn)
+        (si, ss, sl, so), band, counts, mpn = self._topk_exchange(3, k)
         N, n_viol, n_strong = (int(v) for v in counts)
         k = min(k, N)
         si, sl, so = si[:k], sl[:k], so[:k]
-        t = self._t("gather+merge1", t)
+        t = self._t("topk1+exchange+merge", t)
         all_walked = n_strong < k or k == 0
         pobj, pidx = (0.0, 0) if all_walked else (float(so[k - 1]), int(si[k - 1]))
         big_m = float(getattr(eng, "big_m", 1000.0))
@@ -178,10 +201,7 @@ class ShardedSelector(object):
             # the k strong elements up to the pivot are re-scored obj + big_m and nothing else can reach them
             # (combined_is_strong_prefix in capi.cu): the merged strong list is the answer, no second pass
             return pack((si, so + big_m, sl, so), band, counts, new_strat, 3, (pobj, pidx, False))
-        top = eng.topk(4, k, pobj, pidx, 1 if all_walked else 0)
-        band2 = self._band()
-        t = self._t("topk2", t)
-        top, band2, _, _ = self._gather_merge(4, k, top, band2, True)
+        top, band2, _, _ = self._topk_exchange(4, k, (pobj, pidx, 1 if all_walked else 0), want_counts=False)
         band2["n_unc_lam"], band2["n_unc_obj"] = band["n_unc_lam"], band["n_unc_obj"]
-        self._t("gather+merge2", t)
+        self._t("topk2+exchange+merge", t)
         return pack(top, band2, counts, new_strat, 4, (pobj, pidx, bool(all_walked)))
