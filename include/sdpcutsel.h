@@ -126,6 +126,14 @@ int sdpcs_get_cover_rows(sdpcs_ctx *ctx, int16_t *out_idx, int64_t cap_rows);
  * once; set it again to choose another shard. */
 int sdpcs_cover_restrict(sdpcs_ctx *ctx, int64_t begin, int64_t end);
 
+/* Cover algebra of the QCQP caller on the device (CutSolverQCQP.__get_vertex_cover,
+ * cut_select_qcqp.py:319-333: `[el for el in agg_list_cons if el in agg_list]` and its complement, O(N^2) list scans in
+ * the reference).  Keeps the candidates of ctx's list cover that occur in other's list cover (keep_members = 1:
+ * P(E_m) intersected with P(E_0), in P(E_m) order) or that do not (keep_members = 0: the difference); both contexts hold
+ * covers of the same instance on the same device.  *out_N (may be NULL) = candidates left; their agg_idx is their new
+ * position (+ agg_offset). */
+int sdpcs_cover_filter(sdpcs_ctx *ctx, const sdpcs_ctx *other, int keep_members, int64_t *out_N);
+
 int sdpcs_num_candidates(const sdpcs_ctx *ctx, int64_t *N);
 
 /* Score every candidate of the cover at the LP point vars_values = [X upper-tri row-major | x]

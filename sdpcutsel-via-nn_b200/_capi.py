@@ -21,7 +21,7 @@ EXPORTS = [
     "sdpcs_select", "sdpcs_unrank", "sdpcs_binom", "sdpcs_gen_cuts", "sdpcs_eigendecomp", "sdpcs_set_tri_pattern",
     "sdpcs_triangles", "sdpcs_nn_eval", "sdpcs_nn_debug_layer", "sdpcs_fp64_peak",
     "sdpcs_set_cover_pattern", "sdpcs_get_cover_rows", "sdpcs_cover_restrict", "sdpcs_gen_cuts_csr", "sdpcs_triangle_rows_csr", "sdpcs_dense_eigcuts", "sdpcs_max_pos_nonviolated",
-    "sdpcs_last_band", "sdpcs_topk_pack_dev", "sdpcs_merge_packed_dev",
+    "sdpcs_last_band", "sdpcs_topk_pack_dev", "sdpcs_merge_packed_dev", "sdpcs_cover_filter",
 ]
 
 NN_TCGEN05, NN_DMMA = 0, 1
@@ -161,6 +161,12 @@ class Engine(object):
     def cover_restrict(self, begin, end):
         """Keep the candidates [begin, end) of the current cover (this rank's shard); agg_idx values are unchanged."""
         self._ck(self._lib.sdpcs_cover_restrict(self._ctx, c_i64(begin), c_i64(end)))
+
+    def cover_filter(self, other, keep_members=True):
+        """Cover algebra on the device (sdpcs_cover_filter): keep the candidates that (do not) occur in `other`'s list cover."""
+        N = c_i64()
+        self._ck(self._lib.sdpcs_cover_filter(self._ctx, other._ctx, c_int(1 if keep_members else 0), ctypes.byref(N)))
+        return N.value
 
     def cover_rows(self):
         """The current list cover as (N, rho) int16 rows padded with -1 (agg_list[i][0] of the reference)."""

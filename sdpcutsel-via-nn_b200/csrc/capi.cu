@@ -639,6 +639,85 @@ extern "C" int sdpcs_cover_restrict(sdpcs_ctx* ctx, int64_t begin, int64_t end)
     return SDPCS_OK;
 }
 
+static int scan_exclusive(sdpcs_ctx* ctx, const int* d_in, i64 n, i64* d_out, i64* d_sums, i64* d_total)
+{
+    const i64 nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (nb > 0) k_scan_block<<<(unsigned)nb, 256, 0, ctx->stream>>>(d_in, n, d_out, d_sums);
+    k_scan_sums<<<1, 1024, 0, ctx->stream>>>(d_sums, nb, d_total);
+    if (nb > 0) k_scan_add<<<(unsigned)nb, 256, 0, ctx->stream>>>(d_out, n, d_sums);
+    CU(cudaGetLastError());
+    return SDPCS_OK;
+}
+
+// Cover algebra of the QCQP caller (cut_select_qcqp.py:319-333) on the device: keep the candidates of this context's list
+// cover that also occur in `other`'s list cover (keep_members = 1: intersection) or that do not (0: difference), in
+// their order; agg_idx is renumbered 0..N'-1 (+ agg_offset).
+extern "C" int sdpcs_cover_filter(sdpcs_ctx* ctx, const sdpcs_ctx* other, int keep_members, int64_t* out_N)
+{
+    if (!ctx || !other) return SDPCS_ERR_INVALID;
+    if (ctx->mode != 2 || other->mode != 2) return ctx->fail(SDPCS_ERR_STATE, "both contexts need a list cover (sdpcs_set_cover_pattern / _list)");
+    if (ctx->restricted || other->restricted) return ctx->fail(SDPCS_ERR_STATE, "cover algebra needs unrestricted covers");
+    if (ctx->device != other->device || ctx->n != other->n) return ctx->fail(SDPCS_ERR_INVALID, "covers of different instances / devices");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(other->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const i64 N = ctx->N;
+    ctx->have = 0;
+    if (N == 0) { if (out_N) *out_N = 0; return SDPCS_OK; }
+    i64 maxNd = 0;
+    for (int d = 2; d <= 5; ++d) maxNd = std::max(maxNd, ctx->Nd[d]);
+    const i64 nb = (std::max(N, maxNd) + SCAN_TILE - 1) / SCAN_TILE + 1;
+    // scratch: keep_all[N] | all_scan[N] | keep_cls[maxNd] | cls_scan[maxNd] | sums[nb] | totals[2]
+    const size_t o_all = 0, o_ascan = (o_all + 4 * (size_t)N + 15) & ~(size_t)15, o_kcls = o_ascan + 8 * (size_t)N,
+                 o_cscan = (o_kcls + 4 * (size_t)maxNd + 15) & ~(size_t)15, o_sums = o_cscan + 8 * (size_t)maxNd, o_tot = o_sums + 8 * (size_t)nb;
+    int rc = ensure_scratch(ctx, o_tot + 16);
+    if (rc) return rc;
+    char* sc = static_cast<char*>(ctx->d_scratch);
+    int* keep_all = reinterpret_cast<int*>(sc + o_all);
+    i64* all_scan = reinterpret_cast<i64*>(sc + o_ascan);
+    int* keep_cls = reinterpret_cast<int*>(sc + o_kcls);
+    i64* cls_scan = reinterpret_cast<i64*>(sc + o_cscan);
+    i64* sums = reinterpret_cast<i64*>(sc + o_sums);
+    i64* totals = reinterpret_cast<i64*>(sc + o_tot);
+    CU(cudaMemsetAsync(keep_all, 0, 4 * (size_t)N, ctx->stream));
+    // pass 1: global keep flags (by position) from every size class
+    for (int d = 2; d <= 5; ++d) {
+        if (!ctx->Nd[d]) continue;
+        const unsigned grid = (unsigned)std::min<i64>((ctx->Nd[d] + 255) / 256, (i64)ctx->sms * 8);
+        k_cover_member<<<grid, 256, 0, ctx->stream>>>(ctx->d_idx[d], ctx->d_pos[d], ctx->Nd[d], d, other->d_idx[d], other->Nd[d], keep_members,
+                                                      keep_cls, keep_all);
+    }
+    if ((rc = scan_exclusive(ctx, keep_all, N, all_scan, sums, totals))) return rc;
+    i64 newN = 0;
+    CU(cudaMemcpyAsync(&newN, totals, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    // pass 2: per class flags again (the scratch flag array is shared), class scan, compaction into fresh arrays
+    for (int d = 2; d <= 5; ++d) {
+        if (!ctx->Nd[d]) continue;
+        const unsigned grid = (unsigned)std::min<i64>((ctx->Nd[d] + 255) / 256, (i64)ctx->sms * 8);
+        k_cover_member<<<grid, 256, 0, ctx->stream>>>(ctx->d_idx[d], ctx->d_pos[d], ctx->Nd[d], d, other->d_idx[d], other->Nd[d], keep_members,
+                                                      keep_cls, keep_all);
+        if ((rc = scan_exclusive(ctx, keep_cls, ctx->Nd[d], cls_scan, sums, totals + 1))) return rc;
+        i64 nd = 0;
+        CU(cudaMemcpyAsync(&nd, totals + 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        uint8_t* nidx = nullptr;
+        i64* npos = nullptr;
+        if (nd > 0) {
+            CU(cudaMalloc(&nidx, (size_t)nd * d));
+            CU(cudaMalloc(&npos, (size_t)nd * sizeof(i64)));
+            k_cover_compact<<<grid, 256, 0, ctx->stream>>>(ctx->d_idx[d], ctx->d_pos[d], ctx->Nd[d], d, keep_cls, cls_scan, all_scan, nidx, npos);
+            CU(cudaGetLastError());
+            CU(cudaStreamSynchronize(ctx->stream));
+        }
+        cudaFree(ctx->d_idx[d]); cudaFree(ctx->d_pos[d]);
+        ctx->d_idx[d] = nidx; ctx->d_pos[d] = npos; ctx->Nd[d] = nd; ctx->lo[d] = 0;
+    }
+    ctx->N = newN;
+    if (out_N) *out_N = newN;
+    return SDPCS_OK;
+}
+
 extern "C" int sdpcs_num_candidates(const sdpcs_ctx* ctx, int64_t* N)
 {
     if (!ctx || !N) return SDPCS_ERR_INVALID;

@@ -132,4 +132,105 @@ __global__ void __launch_bounds__(256) k_pos_shift(i64* pos, i64 n, i64 delta)
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) pos[i] -= delta;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Cover algebra on the device (cut_select_qcqp.py:319-333): the reference intersects / subtracts two vertex covers with
+// `el in agg_list` list scans, O(N^2).  Rows of one size class are in lexicographic order in both covers, so membership
+// is a binary search on the rows read as big-endian integers; survivors are compacted with exclusive scans.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 cover_row_key(const uint8_t* r, int size)
+{
+    u64 k = 0;
+    for (int t = 0; t < size; ++t) k = (k << 8) | r[t];
+    return k;
+}
+
+// keep_cls[s] = keep_all[pos[s]] = (row s of `mine` occurs in `other`) == keep_members
+__global__ void __launch_bounds__(256) k_cover_member(const uint8_t* idx, const i64* pos, i64 Nd, int size, const uint8_t* oidx, i64 oNd,
+                                                      int keep_members, int* keep_cls, int* keep_all)
+{
+    for (i64 s = (i64)blockIdx.x * blockDim.x + threadIdx.x; s < Nd; s += (i64)gridDim.x * blockDim.x) {
+        const u64 key = cover_row_key(idx + s * size, size);
+        i64 lo = 0, hi = oNd;
+        while (lo < hi) {
+            const i64 m = (lo + hi) >> 1;
+            if (cover_row_key(oidx + m * size, size) < key) lo = m + 1; else hi = m;
+        }
+        const int member = (lo < oNd && cover_row_key(oidx + lo * size, size) == key) ? 1 : 0;
+        const int keep = (member == (keep_members ? 1 : 0)) ? 1 : 0;
+        keep_cls[s] = keep;
+        keep_all[pos[s]] = keep;
+    }
+}
+
+// exclusive scan of n ints into i64, three kernels: per-block scan (1024 elements per block) + block totals,
+// scan of the totals by one block, add-back
+constexpr int SCAN_TILE = 1024;
+__global__ void __launch_bounds__(256) k_scan_block(const int* in, i64 n, i64* out, i64* sums)
+{
+    __shared__ i64 sh[256];
+    const i64 base = (i64)blockIdx.x * SCAN_TILE + 4 * threadIdx.x;
+    int v[4];
+    i64 local = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { v[j] = (base + j < n) ? in[base + j] : 0; local += v[j]; }
+    sh[threadIdx.x] = local;
+    __syncthreads();
+    for (int off = 1; off < 256; off <<= 1) {
+        const i64 add = (threadIdx.x >= off) ? sh[threadIdx.x - off] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += add;
+        __syncthreads();
+    }
+    i64 run = sh[threadIdx.x] - local;                    // exclusive prefix of this thread inside the block
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (base + j < n) out[base + j] = run;
+        run += v[j];
+    }
+    if (threadIdx.x == 255) sums[blockIdx.x] = sh[255];
+}
+__global__ void __launch_bounds__(1024) k_scan_sums(i64* sums, i64 nb, i64* total)
+{
+    __shared__ i64 sh[1024];
+    __shared__ i64 carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (i64 c0 = 0; c0 < nb; c0 += 1024) {
+        const i64 i = c0 + threadIdx.x;
+        const i64 v = i < nb ? sums[i] : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int off = 1; off < 1024; off <<= 1) {
+            const i64 add = (threadIdx.x >= off) ? sh[threadIdx.x - off] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += add;
+            __syncthreads();
+        }
+        if (i < nb) sums[i] = carry + sh[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += sh[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+__global__ void __launch_bounds__(256) k_scan_add(i64* out, i64 n, const i64* sums)
+{
+    const i64 base = (i64)blockIdx.x * SCAN_TILE + 4 * threadIdx.x;
+    const i64 add = sums[blockIdx.x];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (base + j < n) out[base + j] += add;
+}
+
+__global__ void __launch_bounds__(256) k_cover_compact(const uint8_t* idx, const i64* pos, i64 Nd, int size, const int* keep_cls,
+                                                       const i64* cls_scan, const i64* all_scan, uint8_t* nidx, i64* npos)
+{
+    for (i64 s = (i64)blockIdx.x * blockDim.x + threadIdx.x; s < Nd; s += (i64)gridDim.x * blockDim.x) {
+        if (!keep_cls[s]) continue;
+        const i64 d = cls_scan[s];
+        for (int t = 0; t < size; ++t) nidx[d * size + t] = idx[s * size + t];
+        npos[d] = all_scan[pos[s]];
+    }
+}
+
 }  // namespace sdpcs

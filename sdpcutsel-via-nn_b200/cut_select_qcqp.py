@@ -9,7 +9,7 @@ slicing (not re-sorted, :79), and cut generation that tells the two entry format
 import numpy as np
 
 from . import _capi, cover
-from .cut_select_qp import B200CutSelection, CutSolver
+from .cut_select_qp import B200CutSelection, CutSolver, _as_dense_adj as _dense_adj
 
 
 def _row_keys(idx):
@@ -20,10 +20,13 @@ def _row_keys(idx):
     return k
 
 
-def two_pattern_covers(solver, dim):
+def two_pattern_covers(solver, dim, device_algebra=True):
     """cut_select_qcqp.py:314-334 for any solver object carrying the B200CutSelection surface: sets
     solver._agg_list := P(E_m) intersected with P(E_0) (in P(E_m) order) and returns P(E_m) minus that intersection,
-    where P(E_0) is the cover of the objective pattern (_Q_adj) and P(E_m) that of objective + constraints (_Q_adj_cons)."""
+    where P(E_0) is the cover of the objective pattern (_Q_adj) and P(E_m) that of objective + constraints (_Q_adj_cons).
+    Both covers are built on the device; intersection and difference are taken there too (sdpcs_cover_filter: binary
+    search of every P(E_m) row in P(E_0) + scan compaction) and the index rows come back once for the lazy agg_list views.
+    device_algebra=False keeps the set algebra on the host (numpy, on 45-bit row keys) -- the cross-check in the tests."""
     B200CutSelection._get_sdp_vertex_cover(solver, dim)
     agg_obj = solver._agg_list
     Q_adj = solver._Q_adj
@@ -38,6 +41,17 @@ def two_pattern_covers(solver, dim):
     if agg_obj.is_all:                                   # every element of P(E_m) is in P(E_0)
         solver._agg_list = agg_cons
         return empty
+    if device_algebra and agg_obj._engine is not None and agg_cons._engine is not None and not agg_cons.is_all:
+        eng_obj, eng_int = agg_obj._engine, agg_cons._engine
+        eng_diff = solver._new_engine()
+        eng_diff.set_cover_pattern(dim, _dense_adj(solver._Q_adj_cons, n))
+        eng_int.cover_filter(eng_obj, keep_members=True)
+        eng_diff.cover_filter(eng_obj, keep_members=False)
+        inter = cover.AggList(n, dim, Q_arr, idx=eng_int.cover_rows())
+        diff = cover.AggList(n, dim, Q_arr, idx=eng_diff.cover_rows())
+        inter._engine, diff._engine = eng_int, eng_diff
+        solver._agg_list = inter
+        return diff
     cons_idx = agg_cons.idx if not agg_cons.is_all else \
         _capi.unrank(n, dim, np.arange(len(agg_cons))).astype(np.int16)
     # membership of every P(E_m) row in P(E_0): one 45-bit key per (-1 padded) index row instead of the reference's

@@ -193,3 +193,44 @@ def test_cover_restrict_shards_a_list_cover(capi, blobs, golden, dim):
     allc.cover_restrict(50, 500)                                      # relative to the current range: ranks 150 .. 600
     allc.score(vv, 2)
     assert np.array_equal(allc.scores(lam=False)[1], o_all[150:600])
+
+
+@pytest.mark.parametrize("dim", [3, 4, 5])
+def test_two_cover_algebra_on_the_device(dim):
+    """cut_select_qcqp.py:319-333 (P(E_m) intersected with / minus P(E_0)) on the device vs the host set algebra and vs a
+    literal restatement of the reference's list scans, on sparse objective / constraint patterns (mixed clique sizes)."""
+    import sdpcutsel_via_nn_b200 as pkg
+    from sdpcutsel_via_nn_b200.cut_select_qcqp import two_pattern_covers
+    rng = np.random.default_rng(40 + dim)
+    n = 34
+    obj = np.triu(rng.random((n, n)) < 0.35, 1)
+    cons = obj | np.triu(rng.random((n, n)) < 0.25, 1)
+    adj_obj, adj_cons = (obj | obj.T).astype(np.uint8), (cons | cons.T).astype(np.uint8)
+    Q_arr = rng.integers(-9, 10, n * (n + 1) // 2).astype(np.float64)
+    out = {}
+    for dev in (True, False):
+        cs = pkg.CutSolverQCQP()
+        cs.set_instance(Q_arr, adj_obj, n, dim=dim, Q_adj_cons=adj_cons)
+        diff = two_pattern_covers(cs, dim, device_algebra=dev)
+        out[dev] = (cs._agg_list.idx.copy(), diff.idx.copy(), cs._agg_list, diff, cs)
+    assert np.array_equal(out[True][0], out[False][0]) and np.array_equal(out[True][1], out[False][1])
+    # the reference's own statement of it
+    p0 = set(orc.cover_pattern_E_loops(adj_obj, dim))
+    pm = orc.cover_pattern_E_loops(adj_cons, dim)
+    want_int = [t for t in pm if t in p0]
+    want_diff = [t for t in pm if t not in p0]
+    assert out[True][2].keys() == want_int and out[True][3].keys() == want_diff
+    assert len(want_int) > 0 and len(want_diff) > 0
+    # the filtered covers are live device covers: selection on them works and agrees with the oracle
+    cs = out[True][4]
+    vv = orc.synth_point(n, seed=5)
+    for agg, tuples in ((out[True][2], want_int), (out[True][3], want_diff)):
+        cs._agg_list = agg
+        rl = cs._sel_eigcut_by_ordering_on_measure(1, vv, 1)
+        idx = np.full((len(tuples), dim), -1, dtype=np.int32)
+        sizes = np.array([len(t) for t in tuples])
+        for i, t in enumerate(tuples):
+            idx[i, :len(t)] = t
+        lam_o, _ = orc.score_cover(Q_arr, n, idx, sizes, vv, want_obj=False)
+        order, score = orc.select_feas(lam_o)
+        assert [tuple(e[0]) for e in rl] == [tuples[i] for i in order[:5000]]
