@@ -33,6 +33,7 @@ extern "C" {
 /* selection strategies, numbering of cut_select_qp.py:80-81 */
 #define SDPCS_STRAT_FEAS 1
 #define SDPCS_STRAT_OPT 2
+#define SDPCS_STRAT_EXACT 3 /* optimality by the exact rho-dimensional SDP (Mosek in the reference) */
 #define SDPCS_STRAT_COMB 4
 
 typedef struct sdpcs_ctx sdpcs_ctx;
@@ -60,6 +61,7 @@ typedef struct sdpcs_params {
     double guard_lam;        /* absolute guard on lam_min scores, default 1e-12 */
     double guard_obj;        /* absolute guard on optimality measures, default 1e-9 (mirror: 4e-12 * rho * max|Q_arr|) */
     int64_t band_cap;        /* room for near ties after the k winners, default 65536 entries */
+    double sdp_mu_final;     /* exact SDP measure (strat 3): final barrier parameter, value within d * mu of the optimum; 1e-12 */
 } sdpcs_params;
 
 /* NN engines.  Both evaluate neural_net_{2..5}D (cut_select_qp.py:579-582) to FP64 accuracy:
@@ -138,7 +140,10 @@ int sdpcs_num_candidates(const sdpcs_ctx *ctx, int64_t *N);
 
 /* Score every candidate of the cover at the LP point vars_values = [X upper-tri row-major | x]
  * (cut_select_qp.py:547).  want bit 0: lam_min of [1 x^T; x X]_rho (cut_select_qp.py:643-647, 788-797);
- * bit 1: optimality measure max_elem*(NN(x_rho, Q~_rho) - <Q~_rho, X_rho>) (cut_select_qp.py:573-582).
+ * bit 1: optimality measure max_elem*(NN(x_rho, Q~_rho) - <Q~_rho, X_rho>) (cut_select_qp.py:573-582);
+ * bit 2 (instead of bit 1): the EXACT measure max_elem*(v - <Q~_rho, X_rho>), v = min <Q~_rho, X> over
+ * [[X, x_rho], [x_rho^T, 1]] PSD, diag(X) <= x_rho -- what the reference obtains from Mosek per sub-problem
+ * (strat 3, cut_select_qp.py:555-567, 584-598) -- by a batched barrier solver, value within rho * sdp_mu_final.
  * Scores stay resident on the device for sdpcs_topk / sdpcs_scores.  vars_values == NULL re-uses the LP point
  * already resident on the device from the previous call (device-resident timing). */
 int sdpcs_score(sdpcs_ctx *ctx, const double *vars_values, int want);
@@ -200,7 +205,7 @@ int sdpcs_merge_packed_dev(sdpcs_ctx *ctx, const void *d_gathered, int world, in
                            double *out_obj, int64_t *out_n, int64_t *out_band, double *out_hdr);
 
 /* One-call selection on a single GPU with HOST buffers (upload + score + select + download):
- * the whole of _sel_eigcut_by_ordering_on_measure (cut_select_qp.py:543-654) for strat 1, 2, 4, returning the
+ * the whole of _sel_eigcut_by_ordering_on_measure (cut_select_qp.py:543-654) for strat 1, 2, 3, 4, returning the
  * prefix of length <= k of the ranked list.  out_counts = {N, #violated walked, #strong}; out_new_strat as
  * cut_select_qp.py:629 (strat 4 only, else = strat).  vars_values == NULL: use the resident LP point. */
 int sdpcs_select(sdpcs_ctx *ctx, int strat, const double *vars_values, int64_t k,
@@ -268,6 +273,12 @@ int sdpcs_nn_eval(sdpcs_ctx *ctx, int rho, const double *inputs, int64_t m, doub
 /* Test hook for the TCGEN05 engine: the scaled pre-activations z = -2 log2(e) (W a + b) of tansig layer
  * `layer` (0-based) for m input rows, out_z is m x 64 (neurons beyond the layer width are zero padded). */
 int sdpcs_nn_debug_layer(sdpcs_ctx *ctx, int rho, const double *inputs, int64_t m, int layer, double *out_z);
+
+/* Batched exact SDP values v(x, C) = min <C, X> s.t. [[X, x], [x^T, 1]] PSD, diag(X) <= x for m sub-problems of size d
+ * in 2..5 (the Mosek model of cut_select_qp.py:555-567 and of the training-data sampler utilities.py:40-47).  in: m rows
+ * [x (d) | C upper triangle row-major (d(d+1)/2)] with <C, X> = sum_{i<=j} C_ij X_ij; out[m]; out_iters (may be NULL):
+ * Newton steps taken. */
+int sdpcs_sdp_solve(sdpcs_ctx *ctx, int d, const double *in, int64_t m, double *out, int32_t *out_iters);
 
 /* FP64 roofline denominators measured on this device: DFMA and DMMA.8x8x4 peak TFLOP/s. */
 int sdpcs_fp64_peak(sdpcs_ctx *ctx, double *dfma_tflops, double *dmma_tflops);

@@ -527,3 +527,69 @@ def dense_eigcuts(n, vars_values, thres=THRES_NEG_EIGVAL):
             vals.append(v[i1] * v[i2] * np.where(i1 != i2, 2.0, 1.0))
             rhs.append(-v[0] * v[0])
     return ind, np.array(vals).reshape(len(rhs), n + nb_lifted), np.array(rhs), eigvals
+
+
+# ---------------------------------------------------------------------------------------------
+# exact optimality measure (strat 3 / figure 8): the rho-dimensional SDP the reference solves with Mosek
+# ---------------------------------------------------------------------------------------------
+def sdp_exact_value(C_triu, x, mu_final=1e-13):
+    """v(x, C) = min <C, X> s.t. [[X, x], [x^T, 1]] PSD, diag(X) <= x  -- the Mosek model of cut_select_qp.py:555-567
+    (Z = [[X, x], [x^T, 1]] in the PSD cone, X.diag() <= x, objective sum(Q_sub o X) with Q_sub upper triangular, :592-593)
+    and of utilities.py:40-47.  Mosek is not available here, so this is a restatement of the PROBLEM, not of Mosek's
+    algorithm: the equivalent dual  x^T C x - min{sum y : y >= 0, D C D + Diag(y) PSD}, D = diag(sqrt(x (1 - x))), solved
+    by a barrier method with backtracking line search (numpy, batched), duality gap 2 d mu_final.  Pinned against Mosek's
+    own answers in data_figures/fig8_data.csv (tests/test_oracle_golden.py): 1051 sub-problems, max difference 4.3e-6 --
+    Mosek's tolerance.  C_triu: (m, d(d+1)/2) upper triangle row-major, <C, X> = sum_{i<=j} C_ij X_ij; x: (m, d)."""
+    x = np.asarray(x, dtype=np.float64)
+    m, d = x.shape
+    iu = np.triu_indices(d)
+    C = np.zeros((m, d, d))
+    C[:, iu[0], iu[1]] = np.asarray(C_triu, dtype=np.float64)
+    C = (C + C.transpose(0, 2, 1)) / 2.0
+    s = np.sqrt(np.maximum(x - x * x, 0.0))
+    A = C * s[:, :, None] * s[:, None, :]
+    const = np.einsum("mi,mij,mj->m", x, C, x)
+    y = np.abs(A).sum(axis=2) + 1.0
+    eye = np.eye(d)[None]
+    mu = 1.0
+    while mu > mu_final:
+        mu = max(mu * 0.2, mu_final * 0.999)
+        for _ in range(50):
+            S = A + y[:, :, None] * eye
+            Sinv = np.linalg.inv(S)
+            g = 1.0 - mu * (np.einsum("mii->mi", Sinv) + 1.0 / y)
+            H = mu * (Sinv * Sinv + (1.0 / y ** 2)[:, :, None] * eye)
+            dy = -np.linalg.solve(H, g[:, :, None])[:, :, 0]
+            dec = -(g * dy).sum(axis=1)
+            t = np.ones(m)
+            f0 = y.sum(axis=1) - mu * (np.linalg.slogdet(S)[1] + np.log(y).sum(axis=1))
+            for _ls in range(60):
+                yn = y + t[:, None] * dy
+                ok = (yn > 0).all(axis=1)
+                Sn = A + yn[:, :, None] * eye
+                ok &= np.linalg.eigvalsh(Sn)[:, 0] > 0
+                ld = np.linalg.slogdet(np.where(ok[:, None, None], Sn, eye))[1]
+                fn = np.where(ok, yn.sum(axis=1) - mu * (ld + np.log(np.where(ok[:, None], yn, 1.0)).sum(axis=1)), np.inf)
+                good = fn <= f0 - 0.25 * t * dec
+                if good.all():
+                    break
+                t = np.where(good, t, t * 0.5)
+            y = y + t[:, None] * dy
+            if (dec / mu < 1e-3).all():
+                break
+    return const - y.sum(axis=1) + d * mu
+
+
+def exact_measure(Q_arr, n, idx, sizes, vars_values):
+    """obj_improve of strat 3 for every candidate (cut_select_qp.py:575 + 595): (v - <Q~, X>) * max_elem, cover order."""
+    X_vals, x_vals = split_vars(vars_values, n)
+    out = np.full(idx.shape[0], np.nan)
+    for d in np.unique(sizes):
+        sel = np.nonzero(sizes == d)[0]
+        sub = idx[sel, :d]
+        Xinds, Qs, max_elem = aggregate(Q_arr, n, sub)
+        cur = np.zeros(sel.size)
+        for k in range(Qs.shape[1]):
+            cur = cur + Qs[:, k] * X_vals[Xinds][:, k]
+        out[sel] = (-cur) * max_elem + sdp_exact_value(Qs, x_vals[sub]) * max_elem
+    return out

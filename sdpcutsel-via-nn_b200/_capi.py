@@ -21,7 +21,7 @@ EXPORTS = [
     "sdpcs_select", "sdpcs_unrank", "sdpcs_binom", "sdpcs_gen_cuts", "sdpcs_eigendecomp", "sdpcs_set_tri_pattern",
     "sdpcs_triangles", "sdpcs_nn_eval", "sdpcs_nn_debug_layer", "sdpcs_fp64_peak",
     "sdpcs_set_cover_pattern", "sdpcs_get_cover_rows", "sdpcs_cover_restrict", "sdpcs_gen_cuts_csr", "sdpcs_triangle_rows_csr", "sdpcs_dense_eigcuts", "sdpcs_max_pos_nonviolated",
-    "sdpcs_last_band", "sdpcs_topk_pack_dev", "sdpcs_merge_packed_dev", "sdpcs_cover_filter",
+    "sdpcs_last_band", "sdpcs_topk_pack_dev", "sdpcs_merge_packed_dev", "sdpcs_cover_filter", "sdpcs_sdp_solve",
 ]
 
 NN_TCGEN05, NN_DMMA = 0, 1
@@ -30,7 +30,7 @@ NN_TCGEN05, NN_DMMA = 0, 1
 class Params(ctypes.Structure):
     _fields_ = [("thres_min_opt", c_dbl), ("thres_neg_eigval", c_dbl), ("big_m", c_dbl), ("thres_tri_viol", c_dbl),
                 ("thres_tri_dense", ctypes.c_int32), ("jacobi_sweeps", ctypes.c_int32), ("nn_engine", ctypes.c_int32),
-                ("nn_fused_prep", ctypes.c_int32), ("guard_lam", c_dbl), ("guard_obj", c_dbl), ("band_cap", c_i64)]
+                ("nn_fused_prep", ctypes.c_int32), ("guard_lam", c_dbl), ("guard_obj", c_dbl), ("band_cap", c_i64), ("sdp_mu_final", c_dbl)]
 
 
 class Timings(ctypes.Structure):
@@ -348,6 +348,15 @@ class Engine(object):
         out = np.empty(x.shape[0])
         self._ck(self._lib.sdpcs_nn_eval(self._ctx, c_int(rho), _ptr(x), c_i64(x.shape[0]), _ptr(out)))
         return out
+
+    def sdp_solve(self, d, x, C_triu, with_iters=False):
+        """Exact SDP values v(x, C) for m sub-problems of size d (sdpcs_sdp_solve): x (m, d), C_triu (m, d(d+1)/2) upper
+        triangle row-major with <C, X> = sum_{i<=j} C_ij X_ij."""
+        rows = np.ascontiguousarray(np.concatenate([_f64(x).reshape(-1, d), _f64(C_triu).reshape(-1, d * (d + 1) // 2)], axis=1))
+        m = rows.shape[0]
+        out, its = np.empty(m), np.empty(m, np.int32)
+        self._ck(self._lib.sdpcs_sdp_solve(self._ctx, c_int(d), _ptr(rows), c_i64(m), _ptr(out), _ptr(its)))
+        return (out, its) if with_iters else out
 
     def nn_debug_layer(self, rho, inputs, layer):
         """Test hook: scaled pre-activations of tansig layer `layer` from the tcgen05 engine, (m, 64)."""

@@ -15,6 +15,7 @@
 #include "mlp_i8_kernels.cuh"
 #include "select_kernels.cuh"
 #include "exchange_kernels.cuh"
+#include "sdp_kernels.cuh"
 
 using namespace sdpcs;
 
@@ -52,6 +53,7 @@ struct sdpcs_ctx {
     double *d_lam = nullptr, *d_obj = nullptr;
     i64 score_cap = 0;
     int have = 0;
+    bool obj_exact = false;        // d_obj holds the exact SDP measure (strat 3) instead of the NN measure
     // selection scratch (keys are recomputed from lam / obj in every pass; d_key1 holds the triangle keys only)
     u64* d_key1 = nullptr;
     i64 key_cap = 0;
@@ -249,6 +251,7 @@ extern "C" int sdpcs_default_params(sdpcs_params* p)
     p->guard_lam = 1e-12;
     p->guard_obj = 1e-9;
     p->band_cap = 65536;
+    p->sdp_mu_final = 1e-12;
     return SDPCS_OK;
 }
 
@@ -832,6 +835,15 @@ static int launch_score(sdpcs_ctx* ctx, int want, const uint8_t* idx, const i64*
         CU(cudaGetLastError());
         ctx->tm.score_launches++;
     }
+    if (want & 4) {   // K1+K2 + exact SDP optimality measure (strat 3): batched barrier solver, one sub-problem per thread
+        int occ = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_score_sdp<D>, 128, 0));
+        i64 grid = std::min<i64>((groups + 3) / 4, (i64)ctx->sms * std::max(occ, 1));
+        k_score_sdp<D><<<(unsigned)std::max<i64>(grid, 1), 128, 0, ctx->stream>>>(a, ctx->params.sdp_mu_final > 0 ? ctx->params.sdp_mu_final : 1e-12);
+        CU(cudaGetLastError());
+        ctx->tm.score_launches++;
+        return SDPCS_OK;
+    }
     if ((want & 2) && !a.wfrag) return ctx->fail(SDPCS_ERR_STATE, "NN_" + std::to_string(D) + "D weights not set");
     if ((want & 2) && ctx->params.nn_engine != SDPCS_NN_DMMA) {
         // K1+K2 (k_prep_i8) + K4 on tcgen05 (k_mlp_i8), chunked through the layer-0 digit-image buffer
@@ -865,19 +877,20 @@ static int launch_score_d(sdpcs_ctx* ctx, int d, int want, const uint8_t* idx, c
 static int score_device(sdpcs_ctx* ctx, int want)
 {
     if (!ctx->mode) return ctx->fail(SDPCS_ERR_STATE, "cover not set");
-    if (!(want & 3)) return ctx->fail(SDPCS_ERR_INVALID, "want must have bit 0 (lam) and/or bit 1 (obj)");
+    if (!(want & 7) || (want & ~7) || ((want & 2) && (want & 4)))
+        return ctx->fail(SDPCS_ERR_INVALID, "want: bit 0 (lam), and at most one of bit 1 (NN measure) / bit 2 (exact SDP measure)");
     ctx->tm.score_launches = 0;
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     int rc = SDPCS_OK;
     ctx->ev_nn = false;
-    for (int bit = 1; bit <= 2 && rc == SDPCS_OK; bit <<= 1) {   // all eigenvalue launches, then all NN launches
+    for (int bit = 1; bit <= 4 && rc == SDPCS_OK; bit <<= 1) {   // all eigenvalue launches, then all NN (or exact SDP) launches
         if (!(want & bit)) continue;
-        if (bit == 2) CU(cudaEventRecord(ctx->ev[6], ctx->stream));
+        if (bit >= 2) CU(cudaEventRecord(ctx->ev[6], ctx->stream));
         if (ctx->mode == 1) rc = launch_score_d(ctx, ctx->rho, bit, nullptr, nullptr, ctx->N, ctx->base);
         else
             for (int d = 2; d <= ctx->rho && rc == SDPCS_OK; ++d)
                 rc = launch_score_d(ctx, d, bit, ctx->d_idx[d] + ctx->lo[d] * d, ctx->d_pos[d] + ctx->lo[d], ctx->Nd[d], 0);
-        if (bit == 2 && rc == SDPCS_OK) { CU(cudaEventRecord(ctx->ev[7], ctx->stream)); ctx->ev_nn = true; }
+        if (bit >= 2 && rc == SDPCS_OK) { CU(cudaEventRecord(ctx->ev[7], ctx->stream)); ctx->ev_nn = true; }
     }
     if (rc) return rc;
     if (ctx->i8_used) {
@@ -904,7 +917,8 @@ static int score_device(sdpcs_ctx* ctx, int want)
     }
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     ctx->ev_score = true;
-    ctx->have = want & 3;
+    ctx->have = (want & 1) | ((want & 6) ? 2 : 0);       // the exact SDP measure takes the place of the NN measure in d_obj
+    ctx->obj_exact = (want & 4) != 0;
     return SDPCS_OK;
 }
 
@@ -1242,7 +1256,7 @@ extern "C" int sdpcs_select(sdpcs_ctx* ctx, int strat, const double* vars_values
                             int* out_new_strat)
 {
     if (!ctx) return SDPCS_ERR_INVALID;
-    if (strat != 1 && strat != 2 && strat != 4) return ctx->fail(SDPCS_ERR_INVALID, "strat must be 1, 2 or 4");
+    if (strat < 1 || strat > 4) return ctx->fail(SDPCS_ERR_INVALID, "strat must be 1, 2, 3 or 4");
     if (!ctx->mode) return ctx->fail(SDPCS_ERR_STATE, "cover not set");
     CU(cudaSetDevice(ctx->device));
     k = std::min<i64>(std::max<i64>(k, 0), ctx->N);       // sel_size = min(sel_size, len(agg_list)), cut_select_qp.py:550
@@ -1250,11 +1264,11 @@ extern "C" int sdpcs_select(sdpcs_ctx* ctx, int strat, const double* vars_values
     if (vars_values) {
         if ((rc = upload_vars(ctx, vars_values))) return rc;
     } else if (!ctx->vars_resident) return ctx->fail(SDPCS_ERR_STATE, "vars_values == NULL but no LP point is resident");
-    if ((rc = score_device(ctx, strat == 1 ? 1 : strat == 2 ? 2 : 3))) return rc;
+    if ((rc = score_device(ctx, strat == 1 ? 1 : strat == 2 ? 2 : strat == 3 ? 4 : 3))) return rc;
     int new_strat = strat;
     i64 counts[3] = {ctx->N, 0, 0};
     if (strat != 4) {
-        if ((rc = topk_device(ctx, strat, k, 0.0, 0, 0))) return rc;
+        if ((rc = topk_device(ctx, strat == 3 ? 2 : strat, k, 0.0, 0, 0))) return rc;       // strat 3 ranks like strat 2, by the exact measure
         if ((rc = download_topk(ctx, k, out_idx, out_score, out_lam, out_obj, out_n))) return rc;
         counts[1] = ctx->last_counts[1];
     } else {
@@ -1747,6 +1761,35 @@ extern "C" int sdpcs_nn_debug_layer(sdpcs_ctx* ctx, int rho, const double* input
     if ((rc = read_i8_status(ctx, &st))) return rc;
     if (st) return ctx->fail(SDPCS_ERR_CUDA, st == 1 ? "tcgen05 MLP pipeline timed out (k_mlp_i8)" : "NN input outside (-2, 2)");
     CU(cudaMemcpyAsync(out_z, d_z, (size_t)m * 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SDPCS_OK;
+}
+
+// Batched exact SDP values (strat 3 / figure 8 / training-data sampler): m sub-problems of size d given as rows
+// [x (d) | C upper triangle row-major, off-diagonals with the weight of the pair (d(d+1)/2)] -> v(x, C) (sdp_kernels.cuh)
+extern "C" int sdpcs_sdp_solve(sdpcs_ctx* ctx, int d, const double* in, int64_t m, double* out, int32_t* out_iters)
+{
+    if (!ctx || d < 2 || d > 5 || m < 0 || (m && (!in || !out))) return SDPCS_ERR_INVALID;
+    if (m == 0) return SDPCS_OK;
+    CU(cudaSetDevice(ctx->device));
+    const int w = d + d * (d + 1) / 2;
+    int rc = ensure_scratch(ctx, (size_t)m * (w + 1) * 8 + (size_t)m * 4);
+    if (rc) return rc;
+    double* d_in = (double*)ctx->d_scratch;
+    double* d_out = d_in + (size_t)m * w;
+    int* d_it = (int*)(d_out + m);
+    CU(cudaMemcpyAsync(d_in, in, (size_t)m * w * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const double mu = ctx->params.sdp_mu_final > 0 ? ctx->params.sdp_mu_final : 1e-12;
+    const unsigned grid = (unsigned)((m + 127) / 128);
+    switch (d) {
+    case 2: k_sdp_solve<2><<<grid, 128, 0, ctx->stream>>>(d_in, m, mu, d_out, d_it); break;
+    case 3: k_sdp_solve<3><<<grid, 128, 0, ctx->stream>>>(d_in, m, mu, d_out, d_it); break;
+    case 4: k_sdp_solve<4><<<grid, 128, 0, ctx->stream>>>(d_in, m, mu, d_out, d_it); break;
+    default: k_sdp_solve<5><<<grid, 128, 0, ctx->stream>>>(d_in, m, mu, d_out, d_it); break;
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, d_out, (size_t)m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_iters) CU(cudaMemcpyAsync(out_iters, d_it, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return SDPCS_OK;
 }

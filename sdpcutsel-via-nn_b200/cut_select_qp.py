@@ -3,7 +3,7 @@
 Same method names, argument meaning, return formats and error behaviour as the reference for
     _load_neural_nets              (cut_select_qp.py:284-303)
     _get_sdp_vertex_cover          (cut_select_qp.py:377-541)
-    _sel_eigcut_by_ordering_on_measure (cut_select_qp.py:543-703, strat 1, 2, 4)
+    _sel_eigcut_by_ordering_on_measure (cut_select_qp.py:543-703, strat 1, 2, 3, 4, -1)
     _gen_eigcuts_selected          (cut_select_qp.py:705-755)
     _get_eigendecomp               (cut_select_qp.py:788-797)
     __preprocess_triangle_ineq / __separate_and_add_triangle (cut_select_qp.py:799-863)
@@ -20,8 +20,9 @@ Near ties: the device returns the winners plus every candidate wit
 runs of entries closer than the guard are re-scored with the reference's own arithmetic (numpy eigvalsh / the generated
 NN function, ``neartie.py``) and re-sorted, so that the prefix equals the reference's also on LP vertices where
 thousands of candidates tie; ``RankList.degenerate`` / ``n_near_ties`` report what happened.
-Out of scope and raising NotImplementedError: strat 3 / -1 (Mosek exact SDP), strat 5 (random shuffle),
-ch_ext 1 / 2 (chompack chordal extension).
+strat 3 (exact optimality: the rho-dimensional SDP the reference hands to Mosek) and strat -1 (figure 8: estimate vs
+exact) run on the batched SDP solver of sdp_kernels.cuh.  Out of scope and raising NotImplementedError: strat 5
+(random shuffle), ch_ext 1 / 2 (chompack chordal extension).
 """
 import numpy as np
 
@@ -195,10 +196,12 @@ class B200CutSelection(object):
         return len(agg)
 
     def _sel_eigcut_by_ordering_on_measure(self, strat, vars_values, cut_round, sel_size=0):
-        if strat in (3, 5, -1):
-            raise NotImplementedError("strat %d (exact SDP via Mosek / random / figure 8) is outside the GPU hot path" % strat)
-        if strat not in (1, 2, 4):
-            raise ValueError("strat must be 1 (feasibility), 2 (optimality) or 4 (combined)")
+        if strat == 5:
+            raise NotImplementedError("strat 5 (random shuffle of agg_list) is outside the GPU hot path")
+        if strat not in (1, 2, 3, 4, -1):
+            raise ValueError("strat must be 1 (feasibility), 2 (optimality), 3 (exact SDP), 4 (combined) or -1 (figure 8)")
+        if strat == -1:
+            return self._figure_8(vars_values, cut_round, sel_size)
         agg = self._agg_view()
         eng = self._engine_for(agg)
         N = len(agg)
@@ -227,6 +230,39 @@ class B200CutSelection(object):
         if strat_eff == 4:
             return (int(res["new_strat"]), out)                                    # cut_select_qp.py:629-630
         return out
+
+    _FIG8_MAX_SUBS = 2 * 10 ** 6
+
+    def _figure_8(self, vars_values, cut_round, sel_size):
+        """strat -1 (cut_select_qp.py:660-702): every sub-problem scored by the NN estimate AND by the exact SDP, both
+        complete rankings, overlap of the two selections.  Returns (rank_list, share selected by both, std of the exact
+        measures of the exact selection, this_round_cuts) like the reference."""
+        agg = self._agg_view()
+        eng = self._engine_for(agg)
+        N = len(agg)
+        if N > self._FIG8_MAX_SUBS:
+            raise ValueError("figure-8 mode returns complete rankings; %d sub-problems are too many" % N)
+        sel_size = min(sel_size, N)                                   # cut_select_qp.py:550
+        vars_values = np.ascontiguousarray(vars_values, dtype=np.float64)
+        self._last_vars_values = vars_values
+        eng.score(vars_values, 2)
+        _, est = eng.scores(lam=False)
+        eng.score(None, 4)
+        _, exact = eng.scores(lam=False)
+        o_est = np.argsort(-est, kind="stable")                       # list.sort(key=itemgetter(1), reverse=True)
+        o_ex = np.argsort(-exact, kind="stable")
+        place_ex = np.empty(N, dtype=np.int64)
+        place_ex[o_ex] = np.arange(N)
+        nb_lifted = self._nb_lifted
+        sets, xinds, sizes, pts, Xs = self._entry_columns(agg, o_est + agg.offset, vars_values[nb_lifted:], vars_values[:nb_lifted], True)
+        rank_list = RankList(zip((o_est + agg.offset).tolist(), est[o_est].tolist(), pts, Xs))
+        rank_list.n_total = N
+        by_est = (np.arange(N) < sel_size).astype(int)
+        by_ex = (place_ex[o_est] < sel_size).astype(int)
+        this_round_cuts = [[cut_round, c, a, b, e, x] for c, a, b, e, x in
+                           zip((o_est + agg.offset).tolist(), by_est.tolist(), by_ex.tolist(), est[o_est].tolist(), exact[o_est].tolist())]
+        std_dev_exact = np.std(exact[o_ex[:sel_size]])
+        return rank_list, int((by_est & by_ex).sum()) / sel_size, std_dev_exact, this_round_cuts
 
     def _entry_columns(self, agg, idx, x_vals, X_vals, with_values):
         """Per selected candidate: set_inds list, Xarr_inds list (cut_select_qp.py:530-531), size, and -- for the optimality
@@ -264,6 +300,15 @@ class B200CutSelection(object):
         rescorer = neartie.Rescorer(self._nb_vars, self._Q_arr, vars_values, self._blobs,
                                     lambda idx: self._set_rows(agg, idx), thr_eig=float(self._THRES_NEG_EIGVAL),
                                     thr_opt=float(self._THRES_MIN_OPT), big_m=float(self._BIG_M))
+        if strat == 3:
+            # exact SDP measure: the reference's values come out of Mosek (1e-8-level solver noise), so there is no
+            # reference arithmetic to re-score near ties with; they are counted and reported only
+            raw = sel.select(3, vars_values, k)
+            band_n = int(raw["guard"]["n_band"])
+            near = int(neartie.tie_runs(raw["score"], g_obj).sum()) + band_n
+            res = dict(raw, n_near_ties=near, degenerate=2 if near else 0)
+            res.pop("band", None)
+            return res
         k_try, vv = k, vars_values
         for _ in range(4):
             raw = sel.select(strat, vv, k_try)

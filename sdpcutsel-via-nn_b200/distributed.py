@@ -167,10 +167,10 @@ class ShardedSelector(object):
         mode that produced the list (3: strong-prefix shortcut of the combined rule, scores already + big_m)."""
         eng = self.eng
         k = int(k)
-        if strat not in (1, 2, 4):
-            raise ValueError("strat must be 1, 2 or 4")
+        if strat not in (1, 2, 3, 4):
+            raise ValueError("strat must be 1, 2, 3 or 4")
         t = time.perf_counter()
-        eng.score(vars_values, 1 if strat == 1 else 2 if strat == 2 else 3)
+        eng.score(vars_values, {1: 1, 2: 2, 3: 4, 4: 3}[strat])      # want bits: lam, NN measure, exact SDP measure
 
         def pack(top, band, counts, new_strat, path, pivot=None):
             gi, gs, gl, go = top
@@ -179,9 +179,10 @@ class ShardedSelector(object):
                         band={key: band[key] for key in ("idx", "score", "lam", "obj")}, guard=guard)
 
         if strat != 4:
-            top, band, counts, _ = self._topk_exchange(strat, k)
+            mode = 2 if strat == 3 else strat                          # strat 3 ranks like strat 2, by the exact measure
+            top, band, counts, _ = self._topk_exchange(mode, k)
             self._t("topk+exchange+merge", t)
-            return pack(top, band, counts, strat, strat)
+            return pack(top, band, counts, strat, mode)
         # the pivot of the combined rule needs k <= N; N is only known after the exchange, so gather k rows and cut after
         (si, ss, sl, so), band, counts, mpn = self._topk_exchange(3, k)
         N, n_viol, n_strong = (int(v) for v in counts)

@@ -63,7 +63,7 @@ def test_solver_surface_names():
     assert hasattr(pkg.CutSolverQCQP(), "_CutSolverQCQP__get_vertex_cover")
     assert (cs._THRES_NEG_EIGVAL, cs._BIG_M, cs._SDP_CUTS_PER_ROUND_MAX, cs._TRI_CUTS_PER_ROUND_MAX) == (-1e-15, 1000, 5000, 10000)
     with pytest.raises(NotImplementedError):
-        cs._sel_eigcut_by_ordering_on_measure(3, None, 1)
+        cs._sel_eigcut_by_ordering_on_measure(5, None, 1)
     with pytest.raises(NotImplementedError):
         cs._get_sdp_vertex_cover(3, ch_ext=1)
 

@@ -167,3 +167,22 @@ def test_qcqp_caller_pattern(golden, blobs, dim):
     assert ns == int(golden["qcqp_d%d_s4_newstrat" % dim])
     assert np.array_equal(order[:k], golden["qcqp_d%d_s4_idx" % dim])
     assert np.array_equal(score[:k], golden["qcqp_d%d_s4_score" % dim])
+
+
+def test_exact_sdp_oracle_reproduces_moseks_figure_8_values(golden):
+    """oracle.sdp_exact_value / exact_measure (strat 3, cut_select_qp.py:555-598) against the reference's committed Mosek
+    results of figure 8, round 1 (data_figures/fig8_data.csv -> tests/golden/fig8_exact.npz): 1,051 exact measures within
+    Mosek's own tolerance, the exact selection (100 sub-problems) identical, the published round statistics reproduced."""
+    import os
+    with np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fig8_exact.npz")) as z:
+        f = {k: z[k] for k in z.files}
+    n, Q_arr, adj = inst_arrays(golden, "spar020-100-1")
+    idx, sizes = orc.cover_pattern_E(adj, 3)
+    ex = orc.exact_measure(Q_arr, n, idx, sizes, golden["fig8_vars"])
+    assert np.abs(ex[f["r1_cut_idx"]] - f["r1_exact"]).max() < 1e-5
+    order = np.argsort(-ex, kind="stable")
+    sel = np.zeros(idx.shape[0], dtype=int)
+    sel[order[:100]] = 1
+    assert np.array_equal(sel[f["r1_cut_idx"]], f["r1_sel_exact"])
+    assert (sel[f["r1_cut_idx"]] & f["r1_sel_estim"]).sum() / 100 == f["summary"][0, 2]
+    assert abs(np.std(ex[order[:100]]) - f["summary"][0, 3]) < 1e-5
