@@ -355,6 +355,7 @@ def main():
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--strat", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-screened", action="store_true", help="skip the second measurement in screen-and-refine mode")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the short cfg1 / cfg2 / cfg3 / cfg5 measurements appended at N=1")
     ap.add_argument("--nn-engine", default="tcgen05", choices=["tcgen05", "dmma"],
                     help="NN_rhoD evaluation: int8-sliced tcgen05 contraction (default) or FP64 DMMA")
@@ -465,6 +466,56 @@ def main():
             res_dmma = sel.select(args.strat, None, k)
             eng.set_params(nn_engine=pkg._capi.NN_TCGEN05)
             engines_agree = bool(np.array_equal(res["idx"], res_dmma["idx"]))
+        # ---- screen-and-refine mode (second measurement, not the headline): every candidate scored by the 4-digit
+        # engine, the contenders for the k places re-evaluated by the FP64-accurate engine (ScreenedSelector) ----------
+        scr = None
+        if not args.no_screened and args.nn_engine == "tcgen05" and not wl.get("pattern"):
+            from sdpcutsel_via_nn_b200.distributed import ScreenedSelector
+            fine = pkg._capi.Engine(local_rank)
+            fine.set_stream(stream.cuda_stream)
+            fine.set_weights(rho, blobs[rho])
+            fine.set_instance(n, Q_arr)
+            s_guard = 1e-4 * rho * float(np.abs(Q_arr).max())
+            ssel = ScreenedSelector(eng, fine, sets_of, rho, s_guard, g_obj, device=dev if world > 1 else None)
+            rs = ssel.select(args.strat, vv, k)
+            for _ in range(2):
+                rs = ssel.select(args.strat, None, k)
+            s_score = s_nn = s_select = 0.0
+            barrier()
+            e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e4.record(stream)
+            for _ in range(args.steps):
+                rs = ssel.select(args.strat, None, k)
+                tm = eng.timings()
+                s_score += tm["score_ms"]; s_nn += tm["nn_ms"]; s_select += tm["select_ms"]
+            e5.record(stream)
+            barrier()
+            ms_s_dev = e4.elapsed_time(e5)
+            e6, e7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e6.record(stream)
+            for _ in range(args.steps):
+                raw_s = ssel.select(args.strat, vv, k)
+                rs_e2e = neartie.resolve(raw_s, k, rescorer, 1e-12, g_obj)
+            e7.record(stream)
+            barrier()
+            ms_s_e2e = e6.elapsed_time(e7)
+            ts = torch.tensor([ms_s_dev, ms_s_e2e, s_score / args.steps, s_nn / args.steps, s_select / args.steps], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+            ms_s_dev, ms_s_e2e, s_score, s_nn, s_select = (float(v) for v in ts.cpu())
+            idx_s = np.asarray(rs_e2e["idx"], dtype=np.int64)
+            scr = dict(ms_per_step=ms_s_dev / args.steps, value=N * args.steps / (ms_s_dev * 1e-3), unit="subsets/s",
+                       e2e=dict(value=N * args.steps / (ms_s_e2e * 1e-3), ms_per_step=ms_s_e2e / args.steps),
+                       screen_kernels_ms=s_score, nn_kernels_ms=s_nn, select_ms=s_select,
+                       contenders=ssel.last.get("contenders"), max_screen_error=ssel.last.get("max_screen_error"),
+                       screen_guard=s_guard, fallbacks=ssel.fallbacks,
+                       matches_oracle_golden=golden_check(wl, args.strat, idx_s),
+                       idx_sha256=hashlib.sha256(idx_s.tobytes()).hexdigest(), degenerate=int(rs_e2e["degenerate"]),
+                       note="NOT the headline: tier 1 scores every candidate with k_mlp_i8<.., NS=4> (32-bit fixed point, 10 digit pairs, two "
+                            "TMEM accumulator stages; NN output within ~3e-6 of the reference's, north_star asks 1e-5); tier 2 re-evaluates "
+                            "the contenders (winners + everything within screen_guard of the k-th score) with the FP64-accurate engine; "
+                            "tier 3 = neartie.resolve.  The selected list and its scores are the exact engine's.")
+            eng.set_params(nn_engine=pkg._capi.NN_TCGEN05, guard_obj=g_obj)
         t = torch.tensor([ms_dev, ms_e2e, score_ms / args.steps, nn_ms / args.steps, select_ms / args.steps], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -526,6 +577,8 @@ def main():
                            e2e_matches_resident=bool(np.array_equal(res["idx"], res_e2e["idx"])),
                            tcgen05_and_dmma_engines_select_identically=engines_agree),
         )
+        if scr is not None:
+            out["screened"] = scr
         if sel.prof:
             out["host_phase_ms_per_select"] = {k: 1e3 * v / (args.warmup + 2 * args.steps + (1 if args.nn_engine == "tcgen05" else 0)) for k, v in sel.prof.items()}
         if world == 1 and not args.no_cpu_baseline:

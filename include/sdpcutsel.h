@@ -72,6 +72,12 @@ typedef struct sdpcs_params {
  *   DMMA:    FP64 tensor-core contraction (mma.sync.m8n8k4.f64). */
 #define SDPCS_NN_TCGEN05 0
 #define SDPCS_NN_DMMA 1
+/*   SCREEN:  the same tcgen05 pipeline with 4-digit (32-bit fixed point) operands: 10 digit pairs instead of 28, two
+ *            TMEM accumulator stages; NN outputs accurate to ~1e-7 (north_star asks 1e-5).  Meant as the first tier of a
+ *            screen-and-refine selection: every candidate is scored by it, the contenders for the k places (everything
+ *            within the guard of the k-th score, sdpcs_last_band) are re-evaluated by the FP64-accurate engine, so the
+ *            selection stays the reference's (distributed.ShardedSelector(screen=True), bench.py `screened`). */
+#define SDPCS_NN_SCREEN 2
 
 /* Device timings (ms, CUDA events on the context's stream) of the last sdpcs_score / sdpcs_topk calls. */
 typedef struct sdpcs_timings {

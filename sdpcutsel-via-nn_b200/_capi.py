@@ -24,7 +24,7 @@ EXPORTS = [
     "sdpcs_last_band", "sdpcs_topk_pack_dev", "sdpcs_merge_packed_dev", "sdpcs_cover_filter", "sdpcs_sdp_solve",
 ]
 
-NN_TCGEN05, NN_DMMA = 0, 1
+NN_TCGEN05, NN_DMMA, NN_SCREEN = 0, 1, 2
 
 
 class Params(ctypes.Structure):

@@ -36,6 +36,7 @@ struct sdpcs_ctx {
     double* d_wfrag[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // weights as int8 digit images + FP64 parameter block for the tcgen05 MLP (mlp_i8_kernels.cuh)
     uint8_t* d_wi8[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint8_t* d_wi8s[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // 4-digit images of the screening engine
     uint8_t* d_tiles = nullptr;    // layer-0 digit images of one chunk of candidates
     i64 tiles_cap = 0;             // in bytes
     int* d_status = nullptr;       // device status word of the tcgen05 pipeline
@@ -187,11 +188,12 @@ static bool pack_fragments(const double* blob, i64 len, std::vector<double>& out
 // Row j of a layer is scaled by 2^e >= max|W[j,:]|, rounded to 54 fractional bits and written as 7 balanced
 // base-256 digits (slice 0 = most significant).  oracle/nn_i8_model.py states the same arithmetic.
 // ---------------------------------------------------------------------------------------------------
-template <int D>
+template <int D, int NS>
 static void pack_i8(const double* blob, std::vector<uint8_t>& out)
 {
     using C = NetCfg<D>;
-    using L = I8Smem<C::NHID>;
+    using L = I8Smem<C::NHID, NS>;
+    using G = I8Dig<NS>;
     const int n_in = C::NIN, h = C::H, NL = C::NHID + 1;
     const double* xo = blob + 3;
     const double* p = xo + 2 * n_in;
@@ -204,10 +206,12 @@ static void pack_i8(const double* blob, std::vector<uint8_t>& out)
     const double y_gain = p[0], y_xoff = p[1];
     out.assign(L::GLOBAL_BYTES, 0);
     double* par = reinterpret_cast<double*>(out.data() + L::W_TOTAL);
+    unsigned long long bias = 0;                         // 0x80 in every digit: balanced digits
+    for (int b = 0; b < NS; ++b) bias |= 0x80ull << (8 * b);
     for (int l = 0; l < C::NHID; ++l) {
         const int cols = (l == 0) ? n_in : h, K = (l == 0) ? I8_K0 : 64;
-        const int ea = (l == 0) ? 53 : 54;              // digits carry 8 * rint(a * 2^50) resp. 8 * rint(a * 2^51)
-        uint8_t* img = out.data() + (l == 0 ? 0 : I8_W0_BYTES + (l - 1) * I8_WH_BYTES);
+        const int ea = (l == 0) ? G::KA + 2 : G::KA + 3;  // digits carry 8 * rint(a * 2^(KA-1)) resp. 8 * rint(a * 2^KA)
+        uint8_t* img = out.data() + (l == 0 ? 0 : G::W0_BYTES + (l - 1) * G::WH_BYTES);
         for (int j = 0; j < I8_N; ++j) {
             double mx = 0.0;
             if (j < h) for (int k = 0; k < cols; ++k) mx = std::max(mx, std::fabs(W[l][j * cols + k]));
@@ -215,15 +219,15 @@ static void pack_i8(const double* blob, std::vector<uint8_t>& out)
             if (mx > 0.0) std::frexp(mx, &e);           // mx = f * 2^e, f in [0.5, 1): 2^e > = mx
             for (int k = 0; k < K; ++k) {
                 const double w = (j < h && k < cols) ? W[l][j * cols + k] : 0.0;
-                const long long wint = std::llrint(std::ldexp(w, 54 - e));
-                const unsigned long long u = (unsigned long long)(wint + 0x0080808080808080ll);
-                for (int b = 0; b < I8_NS; ++b) {
+                const long long wint = std::llrint(std::ldexp(w, G::KW - e));
+                const unsigned long long u = (unsigned long long)(wint + (long long)bias);
+                for (int b = 0; b < NS; ++b) {
                     const int digit = (int)((u >> (8 * b)) & 0xFF) - 128;
-                    img[(k / 16) * (I8_NS * I8_N * 16) + (6 - b) * (I8_N * 16) + j * 16 + (k % 16)] = (uint8_t)(int8_t)digit;
+                    img[(k / 16) * (NS * I8_N * 16) + (NS - 1 - b) * (I8_N * 16) + j * 16 + (k % 16)] = (uint8_t)(int8_t)digit;
                 }
             }
-            // z = -2 log2(e) * (W a + b);  W a = 2^(e - 54) * 2^-ea * 2^48 * (sum of the kept digit-pair diagonals)
-            par[L::P_CS + 2 * (l * 64 + j)] = std::ldexp(1.0, e - 54 - ea + 48) * SDPCS_TANSIG_SCALE;
+            // z = -2 log2(e) * (W a + b);  W a = 2^(e - KW) * 2^-ea * 256^(NS-1) * (sum of the kept digit-pair diagonals)
+            par[L::P_CS + 2 * (l * 64 + j)] = std::ldexp(1.0, e - G::KW - ea + 8 * (NS - 1)) * SDPCS_TANSIG_SCALE;
             par[L::P_CS + 2 * (l * 64 + j) + 1] = (j < h) ? SDPCS_TANSIG_SCALE * B[l][j] : 0.0;
         }
     }
@@ -307,6 +311,7 @@ extern "C" int sdpcs_destroy(sdpcs_ctx* ctx)
     for (int d = 0; d < 6; ++d) {
         if (ctx->d_wfrag[d]) cudaFree(ctx->d_wfrag[d]);
         if (ctx->d_wi8[d]) cudaFree(ctx->d_wi8[d]);
+        if (ctx->d_wi8s[d]) cudaFree(ctx->d_wi8s[d]);
         if (ctx->d_idx[d]) cudaFree(ctx->d_idx[d]);
         if (ctx->d_pos[d]) cudaFree(ctx->d_pos[d]);
     }
@@ -367,16 +372,23 @@ extern "C" int sdpcs_set_weights(sdpcs_ctx* ctx, int rho, const double* blob, in
     if (ctx->d_wfrag[rho]) { cudaFree(ctx->d_wfrag[rho]); ctx->d_wfrag[rho] = nullptr; }
     CU(cudaMalloc(&ctx->d_wfrag[rho], frag.size() * sizeof(double)));
     CU(cudaMemcpyAsync(ctx->d_wfrag[rho], frag.data(), frag.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    std::vector<uint8_t> img;
-    switch (rho) {
-    case 2: pack_i8<2>(blob, img); break;
-    case 3: pack_i8<3>(blob, img); break;
-    case 4: pack_i8<4>(blob, img); break;
-    case 5: pack_i8<5>(blob, img); break;
+    for (int screen = 0; screen < 2; ++screen) {
+        std::vector<uint8_t> img;
+        switch (rho * 2 + screen) {
+        case 4: pack_i8<2, I8_NS>(blob, img); break;
+        case 5: pack_i8<2, I8_NS_SCREEN>(blob, img); break;
+        case 6: pack_i8<3, I8_NS>(blob, img); break;
+        case 7: pack_i8<3, I8_NS_SCREEN>(blob, img); break;
+        case 8: pack_i8<4, I8_NS>(blob, img); break;
+        case 9: pack_i8<4, I8_NS_SCREEN>(blob, img); break;
+        case 10: pack_i8<5, I8_NS>(blob, img); break;
+        default: pack_i8<5, I8_NS_SCREEN>(blob, img); break;
+        }
+        uint8_t*& dst = screen ? ctx->d_wi8s[rho] : ctx->d_wi8[rho];
+        if (dst) { cudaFree(dst); dst = nullptr; }
+        CU(cudaMalloc(&dst, img.size()));
+        CU(cudaMemcpy(dst, img.data(), img.size(), cudaMemcpyHostToDevice));
     }
-    if (ctx->d_wi8[rho]) { cudaFree(ctx->d_wi8[rho]); ctx->d_wi8[rho] = nullptr; }
-    CU(cudaMalloc(&ctx->d_wi8[rho], img.size()));
-    CU(cudaMemcpyAsync(ctx->d_wi8[rho], img.data(), img.size(), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return SDPCS_OK;
 }
@@ -748,9 +760,9 @@ constexpr int NN_WARPS = 16;
 
 constexpr i64 I8_CHUNK_TILES = 262144;  // 33.6 M candidates, 5.2 GB of digit images per chunk (7 chunks at cfg4 size)
 
-static int ensure_tiles(sdpcs_ctx* ctx, i64 n_tiles)
+static int ensure_tiles(sdpcs_ctx* ctx, i64 n_tiles, i64 tile_bytes = I8_TILE_BYTES)
 {
-    const i64 want = n_tiles * (i64)I8_TILE_BYTES;
+    const i64 want = n_tiles * tile_bytes;
     if (want <= ctx->tiles_cap && ctx->d_tiles) return SDPCS_OK;
     if (ctx->d_tiles) { cudaFree(ctx->d_tiles); ctx->d_tiles = nullptr; ctx->tiles_cap = 0; }
     CU(cudaMalloc(&ctx->d_tiles, (size_t)want));
@@ -758,11 +770,11 @@ static int ensure_tiles(sdpcs_ctx* ctx, i64 n_tiles)
     return SDPCS_OK;
 }
 
-template <int NHID, int D>
+template <int NHID, int D, int NS = I8_NS>
 static int launch_mlp_i8(sdpcs_ctx* ctx, const MlpI8Args& m)
 {
-    using L = I8Smem<NHID>;
-    auto kern = k_mlp_i8<NHID, D>;
+    using L = I8Smem<NHID, NS>;
+    auto kern = k_mlp_i8<NHID, D, NS>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     const unsigned grid = (unsigned)std::max<i64>(1, std::min<i64>(m.n_tiles, ctx->sms));
     kern<<<grid, I8_THREADS, L::TOTAL, ctx->stream>>>(m);
@@ -772,15 +784,16 @@ static int launch_mlp_i8(sdpcs_ctx* ctx, const MlpI8Args& m)
 
 // optimality measure of the N candidates described by `a` through the tcgen05 int8-sliced MLP, layer-0 digit images
 // staged through HBM in chunks by k_prep_i8 (default: faster today) --
-template <int D>
+template <int D, int NS>
 static int launch_nn_i8_staged(sdpcs_ctx* ctx, const ScoreArgs& a, i64 N)
 {
-    if (!ctx->d_wi8[D]) return ctx->fail(SDPCS_ERR_STATE, "NN_" + std::to_string(D) + "D weights not set");
+    const uint8_t* wimg = (NS == I8_NS) ? ctx->d_wi8[D] : ctx->d_wi8s[D];
+    if (!wimg) return ctx->fail(SDPCS_ERR_STATE, "NN_" + std::to_string(D) + "D weights not set");
     const i64 total_tiles = (N + I8_M - 1) / I8_M;
-    int rc = ensure_tiles(ctx, std::min<i64>(total_tiles, I8_CHUNK_TILES));
+    int rc = ensure_tiles(ctx, std::min<i64>(total_tiles, I8_CHUNK_TILES), I8Dig<NS>::TILE_BYTES);
     if (rc) return rc;
     int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_prep_i8<D>, 256, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_prep_i8<D, NS>, 256, 0));
     for (i64 c0 = 0; c0 < N; c0 += I8_CHUNK_TILES * I8_M) {
         const i64 rows = std::min<i64>(N - c0, I8_CHUNK_TILES * I8_M);
         const i64 nt = (rows + I8_M - 1) / I8_M;
@@ -788,12 +801,12 @@ static int launch_nn_i8_staged(sdpcs_ctx* ctx, const ScoreArgs& a, i64 N)
         pa.s = a; pa.c0 = c0; pa.n_rows = rows; pa.tiles = ctx->d_tiles; pa.status = ctx->d_status;
         const i64 groups = nt * (I8_M / 32);
         const i64 pgrid = std::min<i64>((groups + 7) / 8, (i64)ctx->sms * std::max(occ, 1));
-        k_prep_i8<D><<<(unsigned)std::max<i64>(pgrid, 1), 256, 0, ctx->stream>>>(pa);
+        k_prep_i8<D, NS><<<(unsigned)std::max<i64>(pgrid, 1), 256, 0, ctx->stream>>>(pa);
         CU(cudaGetLastError());
         MlpI8Args m;
-        m.wimg = ctx->d_wi8[D]; m.tiles = ctx->d_tiles; m.n_tiles = nt; m.n_rows = rows; m.out_base = c0;
+        m.wimg = wimg; m.tiles = ctx->d_tiles; m.n_tiles = nt; m.n_rows = rows; m.out_base = c0;
         m.pos = a.pos; m.obj = a.obj; m.dbg_z = nullptr; m.dbg_layer = -1; m.status = ctx->d_status;
-        if ((rc = launch_mlp_i8<NetCfg<D>::NHID, 0>(ctx, m))) return rc;
+        if ((rc = launch_mlp_i8<NetCfg<D>::NHID, 0, NS>(ctx, m))) return rc;
         ctx->tm.score_launches += 2;
     }
     ctx->i8_used = true;
@@ -806,7 +819,8 @@ template <int D>
 static int launch_nn_i8(sdpcs_ctx* ctx, const ScoreArgs& a, i64 N)
 {
     if (!ctx->d_wi8[D]) return ctx->fail(SDPCS_ERR_STATE, "NN_" + std::to_string(D) + "D weights not set");
-    if (!ctx->params.nn_fused_prep) return launch_nn_i8_staged<D>(ctx, a, N);
+    if (ctx->params.nn_engine == SDPCS_NN_SCREEN) return launch_nn_i8_staged<D, I8_NS_SCREEN>(ctx, a, N);
+    if (!ctx->params.nn_fused_prep) return launch_nn_i8_staged<D, I8_NS>(ctx, a, N);
     MlpI8Args m;
     m.wimg = ctx->d_wi8[D]; m.s = a; m.tiles = nullptr; m.n_tiles = (N + I8_M - 1) / I8_M; m.n_rows = N; m.out_base = 0;
     m.pos = a.pos; m.obj = a.obj; m.dbg_z = nullptr; m.dbg_layer = -1; m.status = ctx->d_status;
@@ -1661,23 +1675,33 @@ static int read_i8_status(sdpcs_ctx* ctx, int* st)
 }
 
 // batched forward pass of raw input rows through the tcgen05 engine (sdpcs_nn_eval, sdpcs_nn_debug_layer)
-template <int D>
-static int launch_nn_i8_raw(sdpcs_ctx* ctx, const double* d_in, i64 m, double* d_out, double* d_z, int dbg_layer)
+template <int D, int NS>
+static int launch_nn_i8_raw_ns(sdpcs_ctx* ctx, const double* d_in, i64 m, double* d_out, double* d_z, int dbg_layer)
 {
+    const uint8_t* wimg = (NS == I8_NS) ? ctx->d_wi8[D] : ctx->d_wi8s[D];
     for (i64 c0 = 0; c0 < m; c0 += I8_CHUNK_TILES * I8_M) {
         const i64 rows = std::min<i64>(m - c0, I8_CHUNK_TILES * I8_M);
         const i64 nt = (rows + I8_M - 1) / I8_M;
-        int rc = ensure_tiles(ctx, std::min<i64>((m + I8_M - 1) / I8_M, I8_CHUNK_TILES));
+        int rc = ensure_tiles(ctx, std::min<i64>((m + I8_M - 1) / I8_M, I8_CHUNK_TILES), I8Dig<NS>::TILE_BYTES);
         if (rc) return rc;
         const unsigned pgrid = (unsigned)std::max<i64>(1, std::min<i64>((nt * I8_M + 255) / 256, (i64)ctx->sms * 8));
-        k_prep_i8_raw<D><<<pgrid, 256, 0, ctx->stream>>>(ctx->d_wfrag[D], d_in + c0 * NetCfg<D>::NIN, rows, ctx->d_tiles, ctx->d_status);
+        k_prep_i8_raw<D, NS><<<pgrid, 256, 0, ctx->stream>>>(ctx->d_wfrag[D], d_in + c0 * NetCfg<D>::NIN, rows, ctx->d_tiles, ctx->d_status);
         CU(cudaGetLastError());
         MlpI8Args a;
-        a.wimg = ctx->d_wi8[D]; a.tiles = ctx->d_tiles; a.n_tiles = nt; a.n_rows = rows; a.out_base = c0;
+        a.wimg = wimg; a.tiles = ctx->d_tiles; a.n_tiles = nt; a.n_rows = rows; a.out_base = c0;
         a.pos = nullptr; a.obj = d_out; a.dbg_z = d_z ? d_z + c0 * 64 : nullptr; a.dbg_layer = dbg_layer; a.status = ctx->d_status;
-        if ((rc = launch_mlp_i8<NetCfg<D>::NHID, 0>(ctx, a))) return rc;
+        if ((rc = launch_mlp_i8<NetCfg<D>::NHID, 0, NS>(ctx, a))) return rc;
     }
     return SDPCS_OK;
+}
+
+// batched forward pass of raw input rows through the tcgen05 engine (sdpcs_nn_eval, sdpcs_nn_debug_layer); the screening
+// engine (4 digits) when params.nn_engine says so
+template <int D>
+static int launch_nn_i8_raw(sdpcs_ctx* ctx, const double* d_in, i64 m, double* d_out, double* d_z, int dbg_layer)
+{
+    if (ctx->params.nn_engine == SDPCS_NN_SCREEN) return launch_nn_i8_raw_ns<D, I8_NS_SCREEN>(ctx, d_in, m, d_out, d_z, dbg_layer);
+    return launch_nn_i8_raw_ns<D, I8_NS>(ctx, d_in, m, d_out, d_z, dbg_layer);
 }
 
 template <int D>

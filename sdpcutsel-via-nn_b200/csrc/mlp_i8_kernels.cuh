@@ -29,22 +29,46 @@
 
 namespace sdpcs {
 
-constexpr int I8_NS = 7;                                  // digits per operand
-constexpr int I8_ND = 7;                                  // diagonals kept (s + t <= 6)
+constexpr int I8_NS = 7;                                  // digits per operand of the FP64-accurate engine
+constexpr int I8_NS_SCREEN = 4;                           // digits of the screening engine (32-bit fixed point)
 constexpr int I8_M = 128;                                 // candidates per tile (UMMA M)
 constexpr int I8_N = 64;                                  // neurons (UMMA N); 50-neuron nets are zero padded
 constexpr int I8_K0 = 32;                                 // padded input width (UMMA K of layer 0)
-constexpr int I8_SLOTS = 8;                               // TMEM accumulator ring
-constexpr int I8_A0_BYTES = I8_NS * I8_M * I8_K0;         // 28672: layer-0 A image of a tile
-constexpr int I8_AH_BYTES = I8_NS * I8_M * 64;            // 57344: hidden-layer A image of a tile
+constexpr int I8_SLOTS = 8;                               // barrier slots reserved for the TMEM accumulator stages
 constexpr int I8_AUX_BYTES = I8_M * 16;                   // base[128], max_elem[128]
-// Staged tile in global memory (k_prep_i8 -> TMA): compact -- the 16 leading input digits of every row and slice, then
-// the (at most 4) remaining ones as one word, then aux; the zero padding of the K = 32 image is added in shared memory.
-constexpr int I8_G_MAIN = I8_NS * I8_M * 16;              // 14336
-constexpr int I8_G_TAIL = I8_NS * I8_M * 4;               // 3584
-constexpr int I8_TILE_BYTES = I8_G_MAIN + I8_G_TAIL + I8_AUX_BYTES;   // 19968 bytes per tile (156 B per candidate)
-constexpr int I8_W0_BYTES = I8_NS * I8_N * I8_K0;         // 14336
-constexpr int I8_WH_BYTES = I8_NS * I8_N * 64;            // 28672
+
+// Everything that depends on the number of base-256 digits NS per operand.  NS = 7: 56-bit words, 28 digit pairs
+// (s + t <= 6) on 7 diagonals -- FP64-accurate.  NS = 4: 32-bit words, 10 pairs on 4 diagonals: activations carry 2^-27,
+// the NN output ~1e-7 -- the SCREENING engine (its scores only decide which candidates the exact engine re-evaluates).
+// The diagonals of one step take NS x 64 TMEM columns: two accumulator stages fit for NS = 4 (the MMAs of the next step
+// never wait for the epilogue of this one), one for NS = 7.
+__host__ __device__ constexpr double i8_pow2(int e) { return e <= 0 ? 1.0 : 2.0 * i8_pow2(e - 1); }
+
+template <int NS>
+struct I8Dig {
+    static constexpr int ND = NS;                                      // diagonals kept (s + t <= NS - 1)
+    static constexpr int A0_BYTES = NS * I8_M * I8_K0;                 // layer-0 A image of a tile
+    static constexpr int AH_BYTES = NS * I8_M * 64;                    // hidden-layer A image of a tile
+    // Staged tile in global memory (k_prep_i8 -> TMA): compact -- the 16 leading input digits of every row and slice,
+    // then the (at most 4) remaining ones as one word, then aux; the zero padding of the K = 32 image is added in smem.
+    static constexpr int G_MAIN = NS * I8_M * 16;
+    static constexpr int G_TAIL = NS * I8_M * 4;
+    static constexpr int TILE_BYTES = G_MAIN + G_TAIL + I8_AUX_BYTES;  // NS = 7: 19968 bytes per tile (156 B per candidate)
+    static constexpr int W0_BYTES = NS * I8_N * I8_K0;
+    static constexpr int WH_BYTES = NS * I8_N * 64;
+    static constexpr int STAGES = (2 * NS * I8_N <= 512) ? 2 : 1;     // TMEM accumulator stages
+    static constexpr int KA = 8 * NS - 5;                              // hidden activations: u = 8 rint(a 2^KA), |a| <= 1
+    static constexpr int KW = 8 * NS - 2;                              // weights: rint(w 2^(KW - e)) with 2^e >= max|row|
+    static constexpr double SCALE_H = i8_pow2(KA);                     // 2^51 (NS = 7), 2^27 (NS = 4)
+    static constexpr double SCALE_0 = i8_pow2(KA - 1);                 // layer-0 inputs |p| < 2: one bit less
+};
+constexpr int I8_A0_BYTES = I8Dig<I8_NS>::A0_BYTES;       // 28672
+constexpr int I8_AH_BYTES = I8Dig<I8_NS>::AH_BYTES;       // 57344
+constexpr int I8_G_MAIN = I8Dig<I8_NS>::G_MAIN;           // 14336
+constexpr int I8_G_TAIL = I8Dig<I8_NS>::G_TAIL;           // 3584
+constexpr int I8_TILE_BYTES = I8Dig<I8_NS>::TILE_BYTES;   // 19968
+constexpr int I8_W0_BYTES = I8Dig<I8_NS>::W0_BYTES;       // 14336
+constexpr int I8_WH_BYTES = I8Dig<I8_NS>::WH_BYTES;       // 28672
 constexpr int I8_EPI_WARPS = 16;
 constexpr int I8_THREADS = (I8_EPI_WARPS + 4) * 32;       // 640: 16 epilogue warps + one warp group of helpers (MMA, TMA, 2 idle)
 constexpr int I8_NBAR = 2 * I8_SLOTS + 8;                 // slot_full[8] slot_empty[8] a0_full[2] lane_free[2] act_ready[2] y_ready[2]
@@ -60,11 +84,12 @@ __host__ __device__ constexpr uint32_t i8_idesc(int n)
 #define I8_MAGIC52 6755399441055744.0                     /* 1.5 * 2^52 */
 #define I8_MAGIC52_BITS 0x4338000000000000ll
 
-template <int NHID>
+template <int NHID, int NS = I8_NS>
 struct I8Smem {
-    static constexpr int W_TOTAL = I8_W0_BYTES + (NHID - 1) * I8_WH_BYTES;
-    static constexpr int OFF_A = W_TOTAL;                                  // 2 lanes x I8_AH_BYTES
-    static constexpr int OFF_AUX = OFF_A + 2 * I8_AH_BYTES;                // [lane][buf][256] doubles
+    using G = I8Dig<NS>;
+    static constexpr int W_TOTAL = G::W0_BYTES + (NHID - 1) * G::WH_BYTES;
+    static constexpr int OFF_A = W_TOTAL;                                  // 2 lanes x AH_BYTES
+    static constexpr int OFF_AUX = OFF_A + 2 * G::AH_BYTES;                // [lane][buf][256] doubles
     static constexpr int OFF_PAR = OFF_AUX + 4 * I8_AUX_BYTES;
     // parameter block (doubles): (cs, bs)[NHID][64] interleaved pairs, wout[64] misc[4] tab[256]
     static constexpr int P_CS = 0, P_BS = NHID * 64, P_WOUT = 2 * NHID * 64, P_MISC = P_WOUT + 64, P_TAB = P_MISC + 4;
@@ -92,9 +117,6 @@ struct MlpI8Args {
 
 // Optional pipeline trace (tools/i8_trace.py builds a second library with -DSDPCS_I8_TRACE): CTA 0 stamps clock64 at
 // four points of steps 64 .. 64 + I8_TRACE_STEPS of every warp.  Compiled out of the product library.
-#ifndef I8_EXPF
-#define I8_EXPF 0
-#endif
 #ifdef SDPCS_I8_TRACE
 constexpr int I8_TRACE_STEPS = 96;
 __device__ long long g_i8_trace[I8_EPI_WARPS + 4][I8_TRACE_STEPS][4];
@@ -194,9 +216,6 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint
 }
 __device__ __forceinline__ void umma_i8(uint32_t taddr, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
-#if defined(I8_EXP) && I8_EXP == 7
-    return;                                         // experiment: pipeline and epilogue without tensor-core work
-#endif
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(taddr),
                  "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
                  : "memory");
@@ -304,13 +323,28 @@ __device__ __forceinline__ uint32_t i8_pack4(unsigned long long u0, unsigned lon
     return __byte_perm(t01, t23, 0x5410);
 }
 
-// Write one row (candidate) of a layer-0 tile image: NIN mapminmax'ed inputs -> 7 slices x 32 digit bytes, plus aux.
-// Shared-memory image: [slice s (0 = most significant)][k chunk c = k / 16][row][k % 16]; staged tile: see I8_TILE_BYTES.
-template <int NIN>
+// digit words of four fixed-point values, slice by slice: w[s] holds digit (NS - 1 - s) of u0..u3 (slice 0 = most significant)
+template <int NS>
+__device__ __forceinline__ void i8_pack_slices(unsigned long long u0, unsigned long long u1, unsigned long long u2, unsigned long long u3,
+                                               uint32_t (&w)[NS])
+{
+    if constexpr (NS > 0) w[NS - 1] = i8_pack4<0>(u0, u1, u2, u3);
+    if constexpr (NS > 1) w[NS - 2] = i8_pack4<1>(u0, u1, u2, u3);
+    if constexpr (NS > 2) w[NS - 3] = i8_pack4<2>(u0, u1, u2, u3);
+    if constexpr (NS > 3) w[NS - 4] = i8_pack4<3>(u0, u1, u2, u3);
+    if constexpr (NS > 4) w[NS - 5] = i8_pack4<4>(u0, u1, u2, u3);
+    if constexpr (NS > 5) w[NS - 6] = i8_pack4<5>(u0, u1, u2, u3);
+    if constexpr (NS > 6) w[NS - 7] = i8_pack4<6>(u0, u1, u2, u3);
+}
+
+// Write one row (candidate) of a layer-0 tile image: NIN mapminmax'ed inputs -> NS slices x 32 digit bytes, plus aux.
+// Shared-memory image: [slice s (0 = most significant)][k chunk c = k / 16][row][k % 16]; staged tile: see I8Dig::TILE_BYTES.
+template <int NIN, int NS>
 __device__ __forceinline__ void i8_store_row(uint8_t* tile, int row, const double (&p)[NIN], double base, double max_elem,
                                              bool valid, int* status)
 {
-    uint32_t w[I8_NS][5];                        // words of 4 input digits: 16 inputs of the first k chunk + inputs 16..19
+    using G = I8Dig<NS>;
+    uint32_t w[5][NS];                           // words of 4 input digits: 16 inputs of the first k chunk + inputs 16..19
     bool bad = false;
 #pragma unroll
     for (int g = 0; g < 5; ++g) {
@@ -320,25 +354,18 @@ __device__ __forceinline__ void i8_store_row(uint8_t* tile, int row, const doubl
             const int k = 4 * g + t;
             const double pk = (k < NIN && valid) ? p[k < NIN ? k : 0] : 0.0;
             if (k < NIN) bad |= !(fabs(pk) < 2.0);
-            u[t] = i8_quantize(pk, 1125899906842624.0 /* 2^50 */);
+            u[t] = i8_quantize(pk, G::SCALE_0);
         }
-        // byte b of the digit word is slice 6 - b (slice 0 = most significant digit)
-        w[6][g] = i8_pack4<0>(u[0], u[1], u[2], u[3]);
-        w[5][g] = i8_pack4<1>(u[0], u[1], u[2], u[3]);
-        w[4][g] = i8_pack4<2>(u[0], u[1], u[2], u[3]);
-        w[3][g] = i8_pack4<3>(u[0], u[1], u[2], u[3]);
-        w[2][g] = i8_pack4<4>(u[0], u[1], u[2], u[3]);
-        w[1][g] = i8_pack4<5>(u[0], u[1], u[2], u[3]);
-        w[0][g] = i8_pack4<6>(u[0], u[1], u[2], u[3]);
+        i8_pack_slices<NS>(u[0], u[1], u[2], u[3], w[g]);
     }
     if (bad && valid) atomicCAS(status, 0, 2);
     static_assert(NIN <= 20, "the compact tile format keeps one word of the second k chunk");
 #pragma unroll
-    for (int s = 0; s < I8_NS; ++s) {
-        *reinterpret_cast<uint4*>(tile + s * (I8_M * 16) + row * 16) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
-        *reinterpret_cast<uint32_t*>(tile + I8_G_MAIN + s * (I8_M * 4) + row * 4) = w[s][4];     // inputs 16..19
+    for (int s = 0; s < NS; ++s) {
+        *reinterpret_cast<uint4*>(tile + s * (I8_M * 16) + row * 16) = make_uint4(w[0][s], w[1][s], w[2][s], w[3][s]);
+        *reinterpret_cast<uint32_t*>(tile + G::G_MAIN + s * (I8_M * 4) + row * 4) = w[4][s];     // inputs 16..19
     }
-    double* aux = reinterpret_cast<double*>(tile + I8_G_MAIN + I8_G_TAIL);
+    double* aux = reinterpret_cast<double*>(tile + G::G_MAIN + G::G_TAIL);
     aux[row] = valid ? base : 0.0;
     aux[I8_M + row] = valid ? max_elem : 0.0;
 }
@@ -355,7 +382,7 @@ struct PrepI8Args {
     int* status;
 };
 
-template <int D>
+template <int D, int NS>
 __global__ void __launch_bounds__(256) k_prep_i8(PrepI8Args pa)
 {
     using C = NetCfg<D>;
@@ -414,8 +441,8 @@ __global__ void __launch_bounds__(256) k_prep_i8(PrepI8Args pa)
         for (int q = 0; q < D; ++q) p[q] = __dadd_rn(__dmul_rn(__dsub_rn(xs[q], sxo[q]), sgn[q]), -1.0);
 #pragma unroll
         for (int q = 0; q < T; ++q) p[D + q] = __dadd_rn(__dmul_rn(__dsub_rn(Qs[q], sxo[D + q]), sgn[D + q]), -1.0);
-        uint8_t* tile = pa.tiles + (r / I8_M) * (i64)I8_TILE_BYTES;
-        i8_store_row<C::NIN>(tile, (int)(r % I8_M), p, __dmul_rn(-s, max_elem), max_elem, valid, pa.status);
+        uint8_t* tile = pa.tiles + (r / I8_M) * (i64)I8Dig<NS>::TILE_BYTES;
+        i8_store_row<C::NIN, NS>(tile, (int)(r % I8_M), p, __dmul_rn(-s, max_elem), max_elem, valid, pa.status);
         if (all_mode && g + 1 < g1) {
             if (!(valid && lex_advance<D>(a.n, c, 32))) {
 #pragma unroll
@@ -426,7 +453,7 @@ __global__ void __launch_bounds__(256) k_prep_i8(PrepI8Args pa)
 }
 
 // raw NN inputs in global memory (sdpcs_nn_eval): rows of NIN doubles -> tile images; base = 0, max_elem = 1
-template <int D>
+template <int D, int NS>
 __global__ void __launch_bounds__(256) k_prep_i8_raw(const double* wfrag, const double* in, i64 m, uint8_t* tiles, int* status)
 {
     using C = NetCfg<D>;
@@ -439,7 +466,7 @@ __global__ void __launch_bounds__(256) k_prep_i8_raw(const double* wfrag, const 
             const double v = valid ? in[r * C::NIN + q] : 0.0;
             p[q] = __dadd_rn(__dmul_rn(__dsub_rn(v, __ldg(wfrag + C::OFF_XOFF + q)), __ldg(wfrag + C::OFF_GAIN + q)), -1.0);
         }
-        i8_store_row<C::NIN>(tiles + (r / I8_M) * (i64)I8_TILE_BYTES, (int)(r % I8_M), p, 0.0, 1.0, valid, status);
+        i8_store_row<C::NIN, NS>(tiles + (r / I8_M) * (i64)I8Dig<NS>::TILE_BYTES, (int)(r % I8_M), p, 0.0, 1.0, valid, status);
     }
 }
 
@@ -455,17 +482,6 @@ __device__ __forceinline__ void i8_prep_row_smem(const ScoreArgs& a, const int (
                                                  const double* __restrict__ sxo, const double* __restrict__ sgn, int* status)
 {
     using C = NetCfg<D>;
-#if defined(I8_EXP) && I8_EXP == 8
-    {   // experiment: producers that cost nothing (zero image)
-        uint8_t* rp = img + row * 16;
-        for (int sl = 0; sl < I8_NS; ++sl) {
-            *reinterpret_cast<uint4*>(rp + sl * (I8_M * I8_K0)) = make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint4*>(rp + sl * (I8_M * I8_K0) + I8_M * 16) = make_uint4(0, 0, 0, 0);
-        }
-        aux[row] = 0.0; aux[I8_M + row] = 1.0;
-        return;
-    }
-#endif
     // pass A: max |Q_slice| (the values are re-read in pass B: an L2 hit costs less than 30 live registers here)
     double mx = 0.0;
 #pragma unroll
@@ -532,10 +548,13 @@ __device__ __forceinline__ void i8_prep_row_smem(const ScoreArgs& a, const int (
 // ---------------------------------------------------------------------------------------------------
 // D > 0: candidates come from the instance (the producer warp builds the layer-0 image in shared memory);
 // D = 0: raw network inputs, layer-0 images prepared by k_prep_i8_raw and loaded by TMA (sdpcs_nn_eval).
-template <int NHID, int D>
+template <int NHID, int D, int NS = I8_NS>
 __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
 {
-    using L = I8Smem<NHID>;
+    using L = I8Smem<NHID, NS>;
+    using G = I8Dig<NS>;
+    constexpr int STAGES = G::STAGES;
+    static_assert(D == 0 || NS == I8_NS, "the fused producer writes 7-digit images");
     extern __shared__ __align__(1024) uint8_t sm[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     double* par = reinterpret_cast<double*>(sm + L::OFF_PAR);
@@ -586,16 +605,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
     const i64 npair = (t1 - t0 + 1) / 2;
-    // register re-partitioning (per warp group): the helper warps keep 24 (64 when they gather and slice the inputs themselves) registers, the epilogue warps take 112 (104): 20 x 96 >= 4 x 24 + 16 x 112 per thread -- an increase beyond the pool released by the helpers would block for ever;
-    // with 227 KB of shared memory there is no L1 left for spills, every spilled value is an L2 round trip
-    // (the instruction sits at the head of each role's branch so that ptxas allocates each role within its own budget)
-
-#if defined(I8_EXP) && I8_EXP == 5
-    if (warp >= I8_EPI_WARPS) {                   // experiment: epilogue arithmetic alone, no pipeline
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-        goto done;
-    }
-#endif
+    // register re-partitioning (per warp group): the helper warps keep 24 (64 when they gather and slice the inputs
+    // themselves) registers, the epilogue warps take 112 (104): 20 x 96 >= 4 x 24 + 16 x 112 per thread -- an increase
+    // beyond the pool released by the helpers would block for ever; with 227 KB of shared memory there is no L1 left for
+    // spills, every spilled value is an L2 round trip (the instruction sits at the head of each role's branch so that
+    // ptxas allocates each role within its own budget)
     if (warp > I8_EPI_WARPS + 1 && D == 0) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");      // idle members of the helper warp group (TMA mode)
     } else if (warp >= I8_EPI_WARPS + 1) {
@@ -611,7 +625,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
             // three producer warps: 32-row pass g = 4 (tile - t0) + pass goes to warp g mod 3
             constexpr int NPROD = 3;
             const int pw = warp - (I8_EPI_WARPS + 1);
-            int c[D];
+            int c[D > 0 ? D : 1];
 #pragma unroll
             for (int t = 0; t < D; ++t) c[t] = t;
             bool live = all_mode && t0 * I8_M + pw * 32 + lane < a.n_rows;
@@ -627,7 +641,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                 ok = __all_sync(0xffffffffu, ok);
                 if (!ok) break;
                 I8_STAMP((uint32_t)(g / NPROD), 1);
-                uint8_t* img = sm + L::OFF_A + ln * I8_AH_BYTES;
+                uint8_t* img = sm + L::OFF_A + ln * G::AH_BYTES;
                 double* aux = reinterpret_cast<double*>(sm + L::OFF_AUX + (2 * ln + (cnt & 1)) * I8_AUX_BYTES);
                 const i64 r = tile * I8_M + pass * 32 + lane;
                 const bool valid = r < a.n_rows;
@@ -651,20 +665,20 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                 ok = mbar_wait_relaxed(B_FREE + 8 * ln, (cnt & 1) ^ 1, abort_flag, a.status);
                 ok = __all_sync(0xffffffffu, ok);
                 if (!ok) break;
-                const uint8_t* src = a.tiles + tile * (i64)I8_TILE_BYTES;
-                uint8_t* img = sm + L::OFF_A + ln * I8_AH_BYTES;
+                const uint8_t* src = a.tiles + tile * (i64)G::TILE_BYTES;
+                uint8_t* img = sm + L::OFF_A + ln * G::AH_BYTES;
                 if (elect_one()) {
-                    mbar_expect_tx(B_A0 + 8 * ln, I8_G_MAIN + I8_AUX_BYTES);
+                    mbar_expect_tx(B_A0 + 8 * ln, G::G_MAIN + I8_AUX_BYTES);
 #pragma unroll
-                    for (int sl = 0; sl < I8_NS; ++sl)      // first k chunk of every slice
+                    for (int sl = 0; sl < NS; ++sl)      // first k chunk of every slice
                         tma_load_1d(smem_u32(img + sl * (I8_M * I8_K0)), src + sl * (I8_M * 16), I8_M * 16, B_A0 + 8 * ln);
-                    tma_load_1d(smem_u32(sm + L::OFF_AUX + (2 * ln + (cnt & 1)) * I8_AUX_BYTES), src + I8_G_MAIN + I8_G_TAIL, I8_AUX_BYTES,
+                    tma_load_1d(smem_u32(sm + L::OFF_AUX + (2 * ln + (cnt & 1)) * I8_AUX_BYTES), src + G::G_MAIN + G::G_TAIL, I8_AUX_BYTES,
                                 B_A0 + 8 * ln);
                 }
                 __syncwarp();
                 // second k chunk: one word per row and slice from the staged tile, 12 zero bytes of padding
-                const uint32_t* tail = reinterpret_cast<const uint32_t*>(src + I8_G_MAIN);
-                for (int t = lane; t < I8_NS * I8_M; t += 32)
+                const uint32_t* tail = reinterpret_cast<const uint32_t*>(src + G::G_MAIN);
+                for (int t = lane; t < NS * I8_M; t += 32)
                     *reinterpret_cast<uint4*>(img + (t >> 7) * (I8_M * I8_K0) + I8_M * 16 + (t & (I8_M - 1)) * 16) = make_uint4(__ldg(tail + t), 0, 0, 0);
                 fence_async_smem();
                 __syncwarp();
@@ -675,15 +689,17 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
         if constexpr (D > 0) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         else asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
         // ===== MMA issuer (whole warp walks the schedule and waits, one elected lane issues) =====
-        // One accumulator stage: diagonal d lives in TMEM columns [64 d, 64 d + 64).  The stage is handed to the
-        // epilogue with one commit per step and handed back once every epilogue warp has read it, so the MMAs of
-        // step n+1 (other tile) run while the epilogue warps finalize step n.
+        // Accumulator stage st = step mod STAGES: diagonal d lives in TMEM columns [NS 64 st + 64 d, + 64).  A stage is
+        // handed to the epilogue with one commit per step and handed back once every epilogue warp has read it.  With one
+        // stage (NS = 7) the MMAs of step n+1 (other tile) start when step n has been read and run while the epilogue
+        // warps finalize it; with two stages (NS = 4) they never wait for the epilogue of the step before.
         uint32_t step = 0, actc[2] = {0, 0};
         bool ok = true;
         for (i64 p = 0; p < npair && ok; ++p)
             for (int l = 0; l < NHID && ok; ++l)
                 for (int ln = 0; ln < 2 && ok; ++ln) {
                     if (t0 + 2 * p + ln >= t1) continue;
+                    const uint32_t st = step % STAGES, use = step / STAGES;
                     I8_STAMP(step, 0);
                     if (l == 0) ok = mbar_wait(B_A0 + 8 * ln, (uint32_t)p & 1, abort_flag, a.status);
                     else {
@@ -691,37 +707,38 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                         actc[ln]++;
                     }
                     I8_STAMP(step, 1);
-                    if (ok) ok = mbar_wait(B_EMPTY, (step & 1) ^ 1, abort_flag, a.status);
+                    if (ok) ok = mbar_wait(B_EMPTY + 8 * st, (use & 1) ^ 1, abort_flag, a.status);
                     ok = __all_sync(0xffffffffu, ok);
                     if (!ok) break;
                     I8_STAMP(step, 2);
                     tc_fence_after();
                     if (elect_one()) {
                         // A image: [slice s][k chunk][128 rows][16 B]  -> LBO (between the two k chunks of one MMA) 2048
-                        // W image: [k chunk][slice t][64 rows][16 B]   -> LBO 7 * 1024; the slices t = ta..tb of one k
+                        // W image: [k chunk][slice t][64 rows][16 B]   -> LBO NS * 1024; the slices t = ta..tb of one k
                         //          chunk are 64 (tb - ta + 1) consecutive rows: ONE MMA of N = 64 (tb - ta + 1) forms
                         //          the products of A slice s with all of them and lands them in the adjacent
-                        //          accumulators of the diagonals s + ta .. s + tb.  10 MMAs per k step instead of 28,
-                        //          and the A operand is read 10 times instead of 28.
-                        const uint32_t a_base = smem_u32(sm + L::OFF_A + ln * I8_AH_BYTES);
-                        const uint32_t w_base = smem_u32(sm + (l == 0 ? 0 : I8_W0_BYTES + (l - 1) * I8_WH_BYTES));
+                        //          accumulators of the diagonals s + ta .. s + tb.  NS = 7: 10 MMAs per k step instead
+                        //          of 28, and the A operand is read 10 times instead of 28; NS = 4: 4 MMAs for 10 pairs.
+                        const uint32_t a_base = smem_u32(sm + L::OFF_A + ln * G::AH_BYTES);
+                        const uint32_t w_base = smem_u32(sm + (l == 0 ? 0 : G::W0_BYTES + (l - 1) * G::WH_BYTES));
                         const uint32_t a_slice = (l == 0) ? I8_M * I8_K0 : I8_M * 64;
+                        const uint32_t acc0 = tmem + st * (NS * I8_N);
                         const int ksteps = (l == 0) ? 1 : 2;
                         for (int kk = 0; kk < ksteps; ++kk) {
-                            const uint64_t bd0 = umma_desc(w_base + kk * 2 * (I8_NS * I8_N * 16), I8_NS * I8_N * 16, 128);
+                            const uint64_t bd0 = umma_desc(w_base + kk * 2 * (NS * I8_N * 16), NS * I8_N * 16, 128);
 #pragma unroll
-                            for (int sd = 0; sd < I8_NS; ++sd) {
+                            for (int sd = 0; sd < NS; ++sd) {
                                 const uint64_t ad = umma_desc(a_base + sd * a_slice + kk * 2 * (I8_M * 16), I8_M * 16, 128);
                                 constexpr uint32_t SGN = 1u << 7;
-                                const int nt = I8_NS - sd;                 // weight slices t = 0 .. 6 - sd
+                                const int nt = NS - sd;                    // weight slices t = 0 .. NS - 1 - sd
                                 const int n0 = nt < 4 ? nt : 4;
-                                umma_i8(tmem + sd * I8_N, ad, bd0, i8_idesc(64 * n0) | (sd ? 0u : SGN), (sd | kk) > 0);
+                                umma_i8(acc0 + sd * I8_N, ad, bd0, i8_idesc(64 * n0) | (sd ? 0u : SGN), (sd | kk) > 0);
                                 if (nt > 4)
-                                    umma_i8(tmem + (sd + 4) * I8_N, ad, bd0 + (uint64_t)((4 * I8_N * 16) >> 4),
+                                    umma_i8(acc0 + (sd + 4) * I8_N, ad, bd0 + (uint64_t)((4 * I8_N * 16) >> 4),
                                             i8_idesc(64 * (nt - 4)) | (sd ? 0u : SGN), (sd | kk) > 0);
                             }
                         }
-                        umma_commit(B_FULL);
+                        umma_commit(B_FULL + 8 * st);
                         if (l == NHID - 1) umma_commit(B_FREE + 8 * ln);
                     }
                     __syncwarp();
@@ -734,7 +751,6 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
         // ===== epilogue warps =====
         const int q = warp & 3, cq = warp >> 2;
         const int row = q * 32 + lane;
-        const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + cq * 16;
         const double* tab = par + L::P_TAB;
         uint32_t step = 0;
         bool ok = true;
@@ -743,14 +759,14 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                 for (int ln = 0; ln < 2 && ok; ++ln) {
                     const i64 tile = t0 + 2 * p + ln;
                     if (tile >= t1) continue;
+                    const uint32_t st = step % STAGES, use = step / STAGES;
+                    const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + st * (NS * I8_N) + cq * 16;
                     I8_STAMP(step, 0);
-#if !(defined(I8_EXP) && I8_EXP == 5)
                     if (l == 0)   // acquire the TMA-written aux block of this tile (read in the last layer)
                         ok = mbar_wait(B_A0 + 8 * ln, (uint32_t)p & 1, abort_flag, a.status);
-                    if (ok) ok = mbar_wait(B_FULL, step & 1, abort_flag, a.status);
+                    if (ok) ok = mbar_wait(B_FULL + 8 * st, use & 1, abort_flag, a.status);
                     ok = __all_sync(0xffffffffu, ok);
                     if (!ok) break;
-#endif
                     I8_STAMP(step, 1);
                     tc_fence_after();
 #ifdef SDPCS_I8_QSYNC
@@ -758,61 +774,46 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
 #endif
                     const double2* csbs = reinterpret_cast<const double2*>(par + L::P_CS) + l * 64 + cq * 16;   // (cs, bs) pairs
                     const double* wout = par + L::P_WOUT + cq * 16;
-                    // Phase 1: read the seven diagonals (two batches of TMEM loads, 8 neurons each), recombine them
-                    // exactly in int64 and reduce to the FP64 pre-activations.  The accumulator stage is handed back
-                    // to the MMA issuer as soon as the second batch is in registers.
+                    // Phase 1: read the NS diagonals (two batches of TMEM loads, 8 neurons each), recombine them exactly in
+                    // int64 and reduce to the FP64 pre-activations.  The accumulator stage is handed back to the MMA issuer
+                    // as soon as the second batch is in registers.
                     double z[16];
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
-                        uint32_t v0[8], v1[8], v2[8], v3[8], v4[8], v5[8], v6[8];
-#if defined(I8_EXP) && I8_EXP == 5 && !(I8_EXPF & 1)
+                        uint32_t v[NS][8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            v0[j] = step + j; v1[j] = lane * 3 + j; v2[j] = step * lane; v3[j] = step ^ (j * 77);
-                            v4[j] = lane + 5 * j; v5[j] = step * 9 + lane; v6[j] = j * lane + step;
-                        }
-                        if (false) {
-#else
-                        {
-#endif
-                        tmem_ld8_async(tbase + 0 * I8_N + half * 8, v0);
-                        tmem_ld8_async(tbase + 1 * I8_N + half * 8, v1);
-                        tmem_ld8_async(tbase + 2 * I8_N + half * 8, v2);
-                        tmem_ld8_async(tbase + 3 * I8_N + half * 8, v3);
-                        tmem_ld8_async(tbase + 4 * I8_N + half * 8, v4);
-                        tmem_ld8_async(tbase + 5 * I8_N + half * 8, v5);
-                        tmem_ld8_async(tbase + 6 * I8_N + half * 8, v6);
+                        for (int dg = 0; dg < NS; ++dg) tmem_ld8_async(tbase + dg * I8_N + half * 8, v[dg]);
                         tmem_wait_ld();
-#if defined(I8_EXP) && I8_EXP == 5
-                        if (half == 1 && (I8_EXPF & 4)) { tc_fence_before(); __syncwarp(); }
-#else
                         if (half == 1) {
                             tc_fence_before();
                             __syncwarp();
-                            if (lane == 0) mbar_arrive(B_EMPTY);
+                            if (lane == 0) mbar_arrive(B_EMPTY + 8 * st);
                             I8_STAMP(step, 2);
-                        }
-#endif
                         }
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            // value = accH * 2^32 + accL (exact integers, pre-biased so that the bit pattern is the
-                            // double 1.5 * 2^52 + acc), one rounding; z = -2 log2(e) * (W a + b)
-#if defined(I8_EXP) && (I8_EXP == 3 || I8_EXP == 4)
-                            z[half * 8 + j] = __hiloint2double(0x3fe00000 | (v3[j] & 0xfffff), v6[j] ^ v0[j] ^ v1[j] ^ v2[j] ^ v4[j] ^ v5[j]);
-                            continue;
-#endif
-                            long long accH = I8_MAGIC52_BITS, accL = I8_MAGIC52_BITS;
-                            accH = (long long)(int)v0[j] * 65536ll + accH;
-                            accH = (long long)(int)v1[j] * 256ll + accH;
-                            accH = (long long)(int)v2[j] * 1ll + accH;
-                            accL = (long long)(int)v3[j] * 16777216ll + accL;
-                            accL = (long long)(int)v4[j] * 65536ll + accL;
-                            accL = (long long)(int)v5[j] * 256ll + accL;
-                            accL = (long long)(int)v6[j] * 1ll + accL;
-                            const double dl = __longlong_as_double(accL) - I8_MAGIC52;
-                            const double dh = __longlong_as_double(accH) - I8_MAGIC52;
-                            const double val = fma(dh, 4294967296.0, dl);
+                            // value = sum_d S_d 256^(NS-1-d): exact integers, pre-biased so that the bit pattern is the double
+                            // 1.5 * 2^52 + acc; one rounding; z = -2 log2(e) * (W a + b)
+                            double val;
+                            if constexpr (NS == 7) {
+                                long long accH = I8_MAGIC52_BITS, accL = I8_MAGIC52_BITS;
+                                accH = (long long)(int)v[0][j] * 65536ll + accH;
+                                accH = (long long)(int)v[1][j] * 256ll + accH;
+                                accH = (long long)(int)v[2][j] * 1ll + accH;
+                                accL = (long long)(int)v[3][j] * 16777216ll + accL;
+                                accL = (long long)(int)v[4][j] * 65536ll + accL;
+                                accL = (long long)(int)v[5][j] * 256ll + accL;
+                                accL = (long long)(int)v[6][j] * 1ll + accL;
+                                const double dl = __longlong_as_double(accL) - I8_MAGIC52;
+                                const double dh = __longlong_as_double(accH) - I8_MAGIC52;
+                                val = fma(dh, 4294967296.0, dl);
+                            } else {
+                                static_assert(NS == 7 || NS <= 4, "recombination written for 7 and for <= 4 digits");
+                                long long acc = I8_MAGIC52_BITS;           // |sum| < 2^(24 + 8 (NS - 1)) <= 2^48
+#pragma unroll
+                                for (int dg = 0; dg < NS; ++dg) acc = (long long)(int)v[dg][j] * (1ll << (8 * (NS - 1 - dg))) + acc;
+                                val = __longlong_as_double(acc) - I8_MAGIC52;
+                            }
                             const double2 cb = csbs[half * 8 + j];
                             z[half * 8 + j] = fma(val, cb.x, cb.y);
                         }
@@ -823,62 +824,41 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                     }
                     // Phase 2: tansig, four neurons at a time; the activations are re-sliced and stored as soon as two
                     // groups (8 digit bytes per slice) are ready, or fed to the linear output layer
-                    uint8_t* abuf = sm + L::OFF_A + ln * I8_AH_BYTES + cq * (I8_M * 16) + row * 16;
-                    uint32_t keep[I8_NS];
+                    uint8_t* abuf = sm + L::OFF_A + ln * G::AH_BYTES + cq * (I8_M * 16) + row * 16;
+                    uint32_t keep[NS];
                     double part = 0.0;
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         double zz[4], act[4];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) zz[i] = z[g * 4 + i];
-#if defined(I8_EXP) && (I8_EXP == 1 || I8_EXP == 4)
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) act[i] = zz[i] * 1e-3;
-#else
                         tansig_scaled_vec<4>(zz, act, tab);
-#endif
-#if defined(I8_EXP) && (I8_EXP == 2 || I8_EXP == 4)
-                        if (false) {
-#else
                         if (l < NHID - 1) {
-#endif
                             unsigned long long u[4];
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) u[i] = i8_quantize(act[i], 2251799813685248.0 /* 2^51 */);
-                            uint32_t w[I8_NS];
-                            w[0] = i8_pack4<0>(u[0], u[1], u[2], u[3]);
-                            w[1] = i8_pack4<1>(u[0], u[1], u[2], u[3]);
-                            w[2] = i8_pack4<2>(u[0], u[1], u[2], u[3]);
-                            w[3] = i8_pack4<3>(u[0], u[1], u[2], u[3]);
-                            w[4] = i8_pack4<4>(u[0], u[1], u[2], u[3]);
-                            w[5] = i8_pack4<5>(u[0], u[1], u[2], u[3]);
-                            w[6] = i8_pack4<6>(u[0], u[1], u[2], u[3]);
+                            for (int i = 0; i < 4; ++i) u[i] = i8_quantize(act[i], G::SCALE_H);
+                            uint32_t w[NS];
+                            i8_pack_slices<NS>(u[0], u[1], u[2], u[3], w);      // w[s]: slice s (0 = most significant)
                             if ((g & 1) == 0) {
 #pragma unroll
-                                for (int b = 0; b < I8_NS; ++b) keep[b] = w[b];
+                                for (int b = 0; b < NS; ++b) keep[b] = w[b];
                             } else {
 #pragma unroll
-                                for (int b = 0; b < I8_NS; ++b)
-                                    *reinterpret_cast<uint2*>(abuf + (6 - b) * (I8_M * 64) + (g >> 1) * 8) = make_uint2(keep[b], w[b]);
+                                for (int b = 0; b < NS; ++b)
+                                    *reinterpret_cast<uint2*>(abuf + b * (I8_M * 64) + (g >> 1) * 8) = make_uint2(keep[b], w[b]);
                             }
                         } else {
 #pragma unroll
                             for (int i = 0; i < 4; ++i) part = fma(wout[g * 4 + i], act[i], part);
                         }
                     }
-#if defined(I8_EXP) && I8_EXP == 5
-                    if (l == NHID - 1 && part == 123.456) a.obj[0] = part;
-                    if (true) {
-                        if (I8_EXPF & 2) { fence_async_smem(); __syncwarp(); }
-                    } else
-#endif
                     if (l < NHID - 1) {
                         fence_async_smem();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(B_ACT + 8 * ln);
                     } else {
                         // linear output layer (neural_net_3D.m:61-65, 81-85): partial dot products per column quarter
-                        double* yp = reinterpret_cast<double*>(sm + L::OFF_A + ln * I8_AH_BYTES + I8_A0_BYTES);
+                        double* yp = reinterpret_cast<double*>(sm + L::OFF_A + ln * G::AH_BYTES + G::A0_BYTES);
                         yp[cq * I8_M + row] = part;
                         __syncwarp();
                         if (lane == 0) mbar_arrive(B_Y + 8 * ln);
@@ -902,9 +882,6 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                     ++step;
                 }
     }
-#if defined(I8_EXP) && I8_EXP == 5
-done:
-#endif
     tc_fence_before();
     __syncthreads();
     if (warp == I8_EPI_WARPS)

@@ -206,3 +206,81 @@ class ShardedSelector(object):
         band2["n_unc_lam"], band2["n_unc_obj"] = band["n_unc_lam"], band["n_unc_obj"]
         self._t("topk2+exchange+merge", t)
         return pack(top, band2, counts, new_strat, 4, (pobj, pidx, bool(all_walked)))
+
+
+class ScreenedSelector(object):
+    """Screen-and-refine selection for the strategies that rank by the NN measure (2 and 4).
+
+    Tier 1 (screen): `engine` scores EVERY candidate of the shard(s) with the 4-digit tcgen05 engine (SDPCS_NN_SCREEN: NN
+    outputs accurate to ~3e-6, ten digit pairs instead of 28, two TMEM stages) and selects with a guard band of
+    `screen_guard` on the measure: the k winners plus every candidate within the guard of the k-th score come back
+    (globally merged when sharded).  Tier 2 (refine): those contenders -- a few thousand of 2.3e8 -- become the list cover
+    of `refine_engine` (FP64-accurate 7-digit engine, same instance and weights) and the SAME selection runs on them;
+    its result carries the usual 1e-9 guard band for tier 3, the reference-arithmetic re-score of neartie.resolve.
+    The selection is the exact engine's provided no candidate's screening error exceeds screen_guard / 2; the guard is
+    ~40 x the largest error observed (2.6e-6 on the NN output), and every call checks the contenders' actual errors:
+    if the largest exceeds screen_guard / 8, or the band did not fit, or the two tiers disagree on the path of the
+    combined rule, the call falls back to one exact pass over everything (`fallbacks` counts them).
+    sets_of: global agg_idx array -> (m, rho) index rows (-1 padded), to build the refine cover."""
+
+    def __init__(self, engine, refine_engine, sets_of, rho, screen_guard, exact_guard, group=None, device=None, local=False):
+        from . import _capi
+        self._capi = _capi
+        self.eng, self.fine_eng, self.sets_of, self.rho = engine, refine_engine, sets_of, int(rho)
+        self.screen_guard, self.exact_guard = float(screen_guard), float(exact_guard)
+        self.coarse = ShardedSelector(engine, group=group, device=device, local=local)
+        self.fine = ShardedSelector(refine_engine, local=True)
+        self.fallbacks = 0
+        self.last = {}
+        self._fine_has_point = False
+        engine.set_params(nn_engine=_capi.NN_SCREEN, guard_obj=self.screen_guard)
+        refine_engine.set_params(nn_engine=_capi.NN_TCGEN05, guard_obj=self.exact_guard)
+
+    @property
+    def prof(self):
+        return self.coarse.prof
+
+    def _exact_pass(self, strat, vars_values, k):
+        self.fallbacks += 1
+        self.eng.set_params(nn_engine=self._capi.NN_TCGEN05, guard_obj=self.exact_guard)
+        try:
+            return self.coarse.select(strat, vars_values, k)
+        finally:
+            self.eng.set_params(nn_engine=self._capi.NN_SCREEN, guard_obj=self.screen_guard)
+
+    def select(self, strat, vars_values, k):
+        if strat not in (2, 4):
+            return self.coarse.select(strat, vars_values, k)         # no NN measure involved: nothing to screen
+        raw = self.coarse.select(strat, vars_values, k)
+        if raw["guard"]["band_open"]:
+            return self._exact_pass(strat, None, k)
+        cand = np.concatenate([raw["idx"], raw["band"]["idx"]])
+        approx = np.concatenate([raw["obj"], raw["band"]["obj"]])
+        order = np.argsort(cand, kind="stable")                       # ascending agg_idx: local position order == global tie-break
+        cand, approx = cand[order], approx[order]
+        self.last = dict(contenders=int(cand.size), screen_band=int(raw["band"]["idx"].size))
+        if cand.size == 0:
+            return raw
+        self.fine_eng.set_cover_list(self.rho, self.sets_of(cand))
+        vv_fine = vars_values if (vars_values is not None or self._fine_has_point) else None
+        if vars_values is None and not self._fine_has_point:
+            raise ValueError("the refine engine has no LP point yet: pass vars_values on the first call")
+        res = self.fine.select(strat, vv_fine, k)
+        self._fine_has_point = True
+        _, exact = self.fine_eng.scores(lam=False)
+        err = float(np.abs(exact - approx).max())
+        self.last.update(max_screen_error=err)
+        unsure_walk = strat == 4 and res["path"] != raw["path"]       # the tiers disagree on how the combined rule was walked
+        if err > self.screen_guard / 8 or unsure_walk:
+            return self._exact_pass(strat, None, k)
+        # back to global candidate indices; counters and the strategy switch are global quantities of tier 1
+        out = dict(res)
+        out["idx"] = cand[res["idx"]]
+        out["band"] = dict(res["band"], idx=cand[res["band"]["idx"]])
+        if res.get("pivot") is not None:
+            out["pivot"] = (res["pivot"][0], int(cand[res["pivot"][1]]) if cand.size else 0, res["pivot"][2])
+        out["counts"], out["new_strat"] = raw["counts"], raw["new_strat"]
+        g = dict(res["guard"])
+        g["n_unc_lam"] = raw["guard"]["n_unc_lam"]
+        out["guard"] = g
+        return out

@@ -141,6 +141,41 @@ def test_whole_cover_selection_equals_the_oracles(capi, blobs, inst, fullsize_go
     assert [int(v) for v in eng.counts()] == [capi.binom(n, rho), int(g[tag + "_n_violated"]), int(g[tag + "_n_strong"])]
 
 
+@pytest.mark.parametrize("rho", [4, 5])
+def test_screen_and_refine_selects_the_oracles_lists(capi, blobs, inst, fullsize_golden, rho):
+    """ScreenedSelector: every candidate scored by the 4-digit engine, the contenders for the 5000 places re-evaluated by
+    the FP64-accurate engine.  The selection must be the oracle's whole-cover list, no fallback, and the observed
+    screening errors of the contenders far inside the guard."""
+    from sdpcutsel_via_nn_b200 import neartie
+    from sdpcutsel_via_nn_b200.distributed import ScreenedSelector
+    n, Q_arr, vv = inst
+    g, tag, k = fullsize_golden, "n%d_rho%d" % (n, rho), 5000
+    eng, fine = _engine(capi, blobs, n, Q_arr, rho), _engine(capi, blobs, n, Q_arr, rho)
+    eng.set_cover_all(rho)
+    exact_guard = max(1e-12, 4e-12 * rho * float(np.abs(Q_arr).max()))
+    screen_guard = 1e-4 * rho * float(np.abs(Q_arr).max())
+    sel = ScreenedSelector(eng, fine, lambda i: capi.unrank(n, rho, i), rho, screen_guard, exact_guard, local=True)
+    rescorer = neartie.Rescorer(n, Q_arr, vv, blobs, lambda i: capi.unrank(n, rho, i))
+    for strat in (2, 4, 1):
+        raw = sel.select(strat, vv, k)
+        res = neartie.resolve(raw, k, rescorer, 1e-12, exact_guard)
+        assert np.array_equal(res["idx"], g["%s_s%d_idx" % (tag, strat)])
+        assert np.abs(res["score"] - g["%s_s%d_score" % (tag, strat)]).max() < (LAM_TOL if strat == 1 else OBJ_TOL)
+        if strat != 1:
+            assert sel.last["contenders"] >= k and sel.last["max_screen_error"] < screen_guard / 8
+    assert res["degenerate"] == 0 and sel.fallbacks == 0
+    r4 = sel.select(4, None, k)
+    assert r4["new_strat"] == int(g[tag + "_s4_newstrat"]) and [int(v) for v in r4["counts"]] == g[tag + "_s4_counts"].tolist()
+    # whole-cover screening error of the measure (the resident obj array of the screening pass vs the exact engine)
+    eng.score(None, 2)
+    _, obj_s = eng.scores(i0=0, i1=2000000, lam=False)
+    ex = _engine(capi, blobs, n, Q_arr, rho)
+    ex.set_cover_all(rho, 0, 2000000)
+    ex.score(vv, 2)
+    _, obj_e = ex.scores(lam=False)
+    assert np.abs(obj_s - obj_e).max() < screen_guard / 8
+
+
 def _nccl_worker(rank, world, port, ret):
     import os
     import torch

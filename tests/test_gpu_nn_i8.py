@@ -180,3 +180,28 @@ def test_fused_producer_is_bit_identical_to_the_staged_images(capi, blobs, golde
             eng.score(golden["mix_vars"], 2)
             got.append(eng.scores(lam=False)[1])
         assert np.array_equal(got[0], got[1])
+
+
+@pytest.mark.parametrize("rho", [2, 3, 4, 5])
+def test_screening_engine_matches_its_integer_model(capi, blobs, rho):
+    """SDPCS_NN_SCREEN: the same pipeline with 4-digit operands and two TMEM accumulator stages.  Layer by layer against the
+    integer model with ns = 4 (exact integer sums: layer 0 agrees to the last bits), outputs within 1e-5 of NNs.so's
+    arithmetic (north_star's NN tolerance; observed ~3e-6), ragged sizes included."""
+    eng = capi.Engine(0)
+    eng.set_weights(rho, blobs[rho])
+    eng.set_params(nn_engine=capi.NN_SCREEN)
+    x = nn_inputs(rho, 700, seed=40 + rho)
+    nhid = int(blobs[rho][1]) - 1
+    for layer in range(nhid):
+        zg = eng.nn_debug_layer(rho, x, layer)
+        _, zm = m8.forward(blobs[rho], x, layer, ns=4)
+        tol = 4e-15 * np.maximum(1.0, np.abs(zm)) if layer == 0 else 1e-6
+        assert np.all(np.abs(zg - zm) <= tol), (rho, layer, np.abs(zg - zm).max())
+    for m in (1, 129, 383, 40000):
+        x = nn_inputs(rho, m, seed=300 + m)
+        y = eng.nn_eval(rho, x)
+        want = orc.nn_eval(blobs[rho], x)
+        assert np.abs(y - want).max() < 1e-5
+        ym, _ = m8.forward(blobs[rho], x[:2000], ns=4)
+        assert np.abs(y[:2000] - ym).max() < 1e-6
+    assert eng.timings()["nn_fallbacks"] == 0
