@@ -96,7 +96,13 @@ struct I8Smem {
     static constexpr int PAR = P_TAB + 256;
     static constexpr int OFF_BAR = OFF_PAR + PAR * 8;
     static constexpr int OFF_XG = OFF_BAR + I8_NBAR * 8 + 16;               // mapminmax xoffset[24], gain[24] (fused producer)
-    static constexpr int TOTAL = OFF_XG + 2 * 24 * 8;
+    // partial sums of the output layer, [lane][tile parity][column quarter][row].  With ONE accumulator stage they live
+    // in the lane's A buffer behind the layer-0 image (no warp can start the next step of that lane before every warp
+    // has finished this one); with TWO stages a fast warp may already be writing the next tile's activations there
+    // while the finalising warp still reads the sums, so they get their own 16 KB.
+    static constexpr int OFF_Y = OFF_XG + 2 * 24 * 8;
+    static constexpr int Y_BYTES = (G::STAGES == 2) ? 2 * 2 * 4 * I8_M * 8 : 0;
+    static constexpr int TOTAL = OFF_Y + Y_BYTES;
     static constexpr int GLOBAL_BYTES = W_TOTAL + PAR * 8;                 // device blob: images then parameters
 };
 
@@ -858,7 +864,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                         if (lane == 0) mbar_arrive(B_ACT + 8 * ln);
                     } else {
                         // linear output layer (neural_net_3D.m:61-65, 81-85): partial dot products per column quarter
-                        double* yp = reinterpret_cast<double*>(sm + L::OFF_A + ln * G::AH_BYTES + G::A0_BYTES);
+                        double* yp = (STAGES == 2) ? reinterpret_cast<double*>(sm + L::OFF_Y) + (2 * ln + ((int)p & 1)) * (4 * I8_M)
+                                                   : reinterpret_cast<double*>(sm + L::OFF_A + ln * G::AH_BYTES + G::A0_BYTES);
                         yp[cq * I8_M + row] = part;
                         __syncwarp();
                         if (lane == 0) mbar_arrive(B_Y + 8 * ln);
