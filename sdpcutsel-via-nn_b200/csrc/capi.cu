@@ -328,7 +328,12 @@ extern "C" int sdpcs_destroy(sdpcs_ctx* ctx)
 extern "C" int sdpcs_set_stream(sdpcs_ctx* ctx, void* s)
 {
     if (!ctx) return SDPCS_ERR_INVALID;
-    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    cudaStream_t next = s ? (cudaStream_t)s : ctx->own_stream;
+    if (next != ctx->stream) {
+        CU(cudaSetDevice(ctx->device));
+        CU(cudaStreamSynchronize(ctx->stream));      // nothing of this context is left running on the stream it leaves
+    }
+    ctx->stream = next;
     return SDPCS_OK;
 }
 

@@ -53,6 +53,15 @@ class ShardedSelector(object):
         self.dev_exchange = (self.world > 1 and device is not None and getattr(device, "type", "cuda") == "cuda"
                              and hasattr(engine, "topk_pack_dev") and not os.environ.get("SDPCS_HOST_EXCHANGE"))
         self._bufs = {}
+        self._xstream = None
+        if self.dev_exchange:
+            # engine kernels and the NCCL collective must be ordered on ONE stream: torch's current stream if it is a real
+            # one, else (legacy default stream, handle 0 -- which the C ABI reads as "use the context's own stream") a
+            # stream of our own.  Set once, before any scoring, so that no work is left behind on another stream.
+            import torch
+            cur = torch.cuda.current_stream(device)
+            self._xstream = cur if cur.cuda_stream != 0 else torch.cuda.Stream(device=device)
+            engine.set_stream(self._xstream.cuda_stream)
 
     def _t(self, name, t0):
         if self.prof is not None:
@@ -84,14 +93,15 @@ class ShardedSelector(object):
         import torch
         rows_cap = k + BAND_ROWS
         if rows_cap not in self._bufs:
-            self._bufs = {rows_cap: (torch.empty((2 + rows_cap) * 4, dtype=torch.float64, device=self.device),
-                                     torch.empty(self.world * (2 + rows_cap) * 4, dtype=torch.float64, device=self.device))}
+            with torch.cuda.stream(self._xstream):
+                self._bufs = {rows_cap: (torch.empty((2 + rows_cap) * 4, dtype=torch.float64, device=self.device),
+                                         torch.empty(self.world * (2 + rows_cap) * 4, dtype=torch.float64, device=self.device))}
         send, recv = self._bufs[rows_cap]
-        eng.set_stream(torch.cuda.current_stream(self.device).cuda_stream)      # the collective is ordered on this stream
-        eng.topk_pack_dev(mode, k, BAND_ROWS, send.data_ptr(), *pivot)
-        self.dist.all_gather_into_tensor(recv, send, group=self.group)
-        idx, sc, lam, obj, nwin, nband, hdr = eng.merge_packed_dev(recv.data_ptr(), self.world, rows_cap, k, mode == 4,
-                                                                   self._guard_of(mode), k + self.world * BAND_ROWS)
+        with torch.cuda.stream(self._xstream):                                   # the collective is ordered on the engine's stream
+            eng.topk_pack_dev(mode, k, BAND_ROWS, send.data_ptr(), *pivot)
+            self.dist.all_gather_into_tensor(recv, send, group=self.group)
+            idx, sc, lam, obj, nwin, nband, hdr = eng.merge_packed_dev(recv.data_ptr(), self.world, rows_cap, k, mode == 4,
+                                                                       self._guard_of(mode), k + self.world * BAND_ROWS)
         band = dict(idx=idx[nwin:], score=sc[nwin:], lam=lam[nwin:], obj=obj[nwin:], n_band=int(nband), band_open=int(hdr[7]),
                     n_unc_lam=int(hdr[5]), n_unc_obj=int(hdr[6]))
         counts = np.array([int(hdr[1]), int(hdr[2]), int(hdr[3])], dtype=np.int64) if want_counts else None
