@@ -37,6 +37,8 @@ def main():
     eng = pkg._capi.Engine(0)
     blob = pkg.nn_weights.load_packed(rho)
     eng.set_weights(rho, blob)
+    if "--screen" in sys.argv:
+        eng.set_params(nn_engine=pkg._capi.NN_SCREEN)
     m = 148 * 48 * 128
     rng = np.random.default_rng(3)
     nin = rho * (rho + 3) // 2

@@ -15,4 +15,4 @@ timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
 timeout 900 ncu --set full --clock-control none --import-source on -k "regex:k_score_feas|k_prep_i8|k_mlp_i8" -c 3 -f -o $O/${TAG}_prof_cfg4 \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $O/${TAG}_ncu2.log 2>&1
 timeout 300 python tools/cover_bench.py > $O/${TAG}_cover_bench.log 2>&1; cat $O/${TAG}_cover_bench.log
-timeout 120 python tools/i8_trace.py --build > /dev/null 2>&1 && timeout 120 python tools/i8_trace.py -q > $O/${TAG}_i8_trace.log 2>&1; head -3 $O/${TAG}_i8_trace.log
+timeout 120 python tools/i8_trace.py -q > $O/${TAG}_i8_trace.log 2>&1; timeout 120 python tools/i8_trace.py -q --screen > $O/${TAG}_i8_trace_screen.log 2>&1; head -3 $O/${TAG}_i8_trace.log $O/${TAG}_i8_trace_screen.log

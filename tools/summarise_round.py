@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Turn the raw outputs of tools/measure_round.sh (gpurun_out/<tag>_*) into the tracked summaries under profiles/.
-    python tools/summarise_round.py r01c v5        (tag of the measurement pass, version suffix of the files)"""
+    python tools/summarise_round.py r01c v5 [r02]  (tag of the measurement pass, version suffix of the files, directory under profiles/)"""
 import collections
 import csv
 import io
@@ -11,9 +11,9 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tag, ver = (sys.argv[1:] + ["r01c", "v5"])[:2]
+tag, ver, rnd = (sys.argv[1:] + ["r01c", "v5", "r01"])[:3]
 G = os.path.join(ROOT, "gpurun_out")
-P = os.path.join(ROOT, "profiles", "r01")
+P = os.path.join(ROOT, "profiles", rnd)
 os.makedirs(P, exist_ok=True)
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0, "nsecond": 1e-6}
 
@@ -100,7 +100,7 @@ for a, b in (("_bench_n1.json", "bench_cfg4_%s_n1_default.json"), ("_bench_n1_dm
     if os.path.exists(f):
         shutil.copy(f, os.path.join(P, b % ver))
 step_bytes = sum(v[1] for v in per_step.values())
-json.dump({"source": "profiles/r01/ncu_launches_cfg4_%s_summary.txt" % ver,
+json.dump({"source": "profiles/%s/ncu_launches_cfg4_%s_summary.txt" % (rnd, ver),
            "kernels": {k: {"ms_per_pass": v[0], "dram_bytes_per_pass": v[1]} for k, v in per_step.items()},
            "score_kernel_dram_bytes_per_launch": step_bytes,
            "note": "one scoring pass over 234,531,275 candidates = 1 x k_score_feas + %g x (k_prep_i8 + k_mlp_i8): dram__bytes_read.sum + " % chunks +
