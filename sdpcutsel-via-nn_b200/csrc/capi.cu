@@ -37,6 +37,7 @@ struct sdpcs_ctx {
     // weights as int8 digit images + FP64 parameter block for the tcgen05 MLP (mlp_i8_kernels.cuh)
     uint8_t* d_wi8[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     uint8_t* d_wi8s[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // 4-digit images of the screening engine
+    bool i8_ok[6] = {false, false, false, false, false, false};   // pre-activations of the net stay inside the range of the tcgen05 engines
     uint8_t* d_tiles = nullptr;    // layer-0 digit images of one chunk of candidates
     i64 tiles_cap = 0;             // in bytes
     int* d_status = nullptr;       // device status word of the tcgen05 pipeline
@@ -188,8 +189,10 @@ static bool pack_fragments(const double* blob, i64 len, std::vector<double>& out
 // Row j of a layer is scaled by 2^e >= max|W[j,:]|, rounded to 54 fractional bits and written as 7 balanced
 // base-256 digits (slice 0 = most significant).  oracle/nn_i8_model.py states the same arithmetic.
 // ---------------------------------------------------------------------------------------------------
+// Returns false if a pre-activation could leave the range the kernel's tansig handles without a clamp (|z| < I8_Z_MAX):
+// the FP64 DMMA engine then serves this net.
 template <int D, int NS>
-static void pack_i8(const double* blob, std::vector<uint8_t>& out)
+static bool pack_i8(const double* blob, std::vector<uint8_t>& out)
 {
     using C = NetCfg<D>;
     using L = I8Smem<C::NHID, NS>;
@@ -208,13 +211,15 @@ static void pack_i8(const double* blob, std::vector<uint8_t>& out)
     double* par = reinterpret_cast<double*>(out.data() + L::W_TOTAL);
     unsigned long long bias = 0;                         // 0x80 in every digit: balanced digits
     for (int b = 0; b < NS; ++b) bias |= 0x80ull << (8 * b);
+    double zmax = 0.0;
     for (int l = 0; l < C::NHID; ++l) {
         const int cols = (l == 0) ? n_in : h, K = (l == 0) ? I8_K0 : 64;
         const int ea = (l == 0) ? G::KA + 2 : G::KA + 3;  // digits carry 8 * rint(a * 2^(KA-1)) resp. 8 * rint(a * 2^KA)
         uint8_t* img = out.data() + (l == 0 ? 0 : G::W0_BYTES + (l - 1) * G::WH_BYTES);
         for (int j = 0; j < I8_N; ++j) {
-            double mx = 0.0;
-            if (j < h) for (int k = 0; k < cols; ++k) mx = std::max(mx, std::fabs(W[l][j * cols + k]));
+            double mx = 0.0, sum = 0.0;
+            if (j < h) for (int k = 0; k < cols; ++k) { mx = std::max(mx, std::fabs(W[l][j * cols + k])); sum += std::fabs(W[l][j * cols + k]); }
+            if (j < h) zmax = std::max(zmax, std::fabs(SDPCS_TANSIG_SCALE) * (sum * (l == 0 ? 2.0 : 1.0) + std::fabs(B[l][j])));
             int e = 0;
             if (mx > 0.0) std::frexp(mx, &e);           // mx = f * 2^e, f in [0.5, 1): 2^e > = mx
             for (int k = 0; k < K; ++k) {
@@ -236,6 +241,7 @@ static void pack_i8(const double* blob, std::vector<uint8_t>& out)
     par[L::P_MISC + 1] = y_gain;
     par[L::P_MISC + 2] = y_xoff;
     for (int j = 0; j < 256; ++j) par[L::P_TAB + j] = (double)exp2l((long double)j / 256.0L);
+    return zmax < I8_Z_MAX;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -377,18 +383,21 @@ extern "C" int sdpcs_set_weights(sdpcs_ctx* ctx, int rho, const double* blob, in
     if (ctx->d_wfrag[rho]) { cudaFree(ctx->d_wfrag[rho]); ctx->d_wfrag[rho] = nullptr; }
     CU(cudaMalloc(&ctx->d_wfrag[rho], frag.size() * sizeof(double)));
     CU(cudaMemcpyAsync(ctx->d_wfrag[rho], frag.data(), frag.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->i8_ok[rho] = true;
     for (int screen = 0; screen < 2; ++screen) {
         std::vector<uint8_t> img;
+        bool in_range = false;
         switch (rho * 2 + screen) {
-        case 4: pack_i8<2, I8_NS>(blob, img); break;
-        case 5: pack_i8<2, I8_NS_SCREEN>(blob, img); break;
-        case 6: pack_i8<3, I8_NS>(blob, img); break;
-        case 7: pack_i8<3, I8_NS_SCREEN>(blob, img); break;
-        case 8: pack_i8<4, I8_NS>(blob, img); break;
-        case 9: pack_i8<4, I8_NS_SCREEN>(blob, img); break;
-        case 10: pack_i8<5, I8_NS>(blob, img); break;
-        default: pack_i8<5, I8_NS_SCREEN>(blob, img); break;
+        case 4: in_range = pack_i8<2, I8_NS>(blob, img); break;
+        case 5: in_range = pack_i8<2, I8_NS_SCREEN>(blob, img); break;
+        case 6: in_range = pack_i8<3, I8_NS>(blob, img); break;
+        case 7: in_range = pack_i8<3, I8_NS_SCREEN>(blob, img); break;
+        case 8: in_range = pack_i8<4, I8_NS>(blob, img); break;
+        case 9: in_range = pack_i8<4, I8_NS_SCREEN>(blob, img); break;
+        case 10: in_range = pack_i8<5, I8_NS>(blob, img); break;
+        default: in_range = pack_i8<5, I8_NS_SCREEN>(blob, img); break;
         }
+        ctx->i8_ok[rho] = ctx->i8_ok[rho] && in_range;   // otherwise the FP64 DMMA engine serves this net
         uint8_t*& dst = screen ? ctx->d_wi8s[rho] : ctx->d_wi8[rho];
         if (dst) { cudaFree(dst); dst = nullptr; }
         CU(cudaMalloc(&dst, img.size()));
@@ -864,7 +873,7 @@ static int launch_score(sdpcs_ctx* ctx, int want, const uint8_t* idx, const i64*
         return SDPCS_OK;
     }
     if ((want & 2) && !a.wfrag) return ctx->fail(SDPCS_ERR_STATE, "NN_" + std::to_string(D) + "D weights not set");
-    if ((want & 2) && ctx->params.nn_engine != SDPCS_NN_DMMA) {
+    if ((want & 2) && ctx->params.nn_engine != SDPCS_NN_DMMA && ctx->i8_ok[D]) {
         // K1+K2 (k_prep_i8) + K4 on tcgen05 (k_mlp_i8), chunked through the layer-0 digit-image buffer
         int rc = launch_nn_i8<D>(ctx, a, N);
         if (rc) return rc;
@@ -1734,7 +1743,7 @@ extern "C" int sdpcs_nn_eval(sdpcs_ctx* ctx, int rho, const double* inputs, int6
     double* d_in = (double*)ctx->d_scratch;
     double* d_out = d_in + (size_t)m * nin;
     CU(cudaMemcpyAsync(d_in, inputs, (size_t)m * nin * 8, cudaMemcpyHostToDevice, ctx->stream));
-    bool dmma = ctx->params.nn_engine == SDPCS_NN_DMMA;
+    bool dmma = ctx->params.nn_engine == SDPCS_NN_DMMA || !ctx->i8_ok[rho];
     for (int attempt = 0; attempt < 2; ++attempt) {
         if (dmma) {
             switch (rho) {

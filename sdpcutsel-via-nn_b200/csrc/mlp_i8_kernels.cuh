@@ -1,4 +1,4 @@
-// K4 on the 5th-generation tensor cores: NN_rhoD as an error-free int8-sliced contraction (tcgen05.mma kind::i8,
+// K4 on the 5th-generation tensor cores: NN_rhoD as an FP64-accurate int8-sliced contraction (tcgen05.mma kind::i8,
 // accumulators in TMEM) instead of FP64 DMMA.  Replaces `nns[d-2][0](input_arr)` (cut_select_qp.py:579-582).
 //
 // Arithmetic (oracle/nn_i8_model.py is the bit-exact CPU statement of it):
@@ -161,13 +161,24 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity)
                  : "memory");
     return ok != 0;
 }
+// same with a suspend-time hint: the warp sleeps in hardware until the phase completes or `ns` nanoseconds have passed,
+// so that a waiting helper warp takes (almost) no issue slots from the epilogue warps of its scheduler
+__device__ __forceinline__ bool mbar_try_hint(uint32_t bar, uint32_t parity, uint32_t ns)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity), "r"(ns)
+                 : "memory");
+    return ok != 0;
+}
 // Bounded wait: a protocol error ends as status = 1 and a clean kernel exit, never as a hung GPU.
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag, int* status)
 {
     if (mbar_try(bar, parity)) return true;
     const long long t0 = clock64();
     while (true) {
-        if (mbar_try(bar, parity)) return true;
+        if (mbar_try_hint(bar, parity, 20000u)) return true;
         if (*abort_flag) return false;
         if (clock64() - t0 > (1ll << 31)) {
             *abort_flag = 1;
@@ -176,22 +187,9 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatil
         }
     }
 }
-// same, for the producer warp that runs a whole tile ahead: back off between polls so that it does not take
-// issue slots from the epilogue warps of its scheduler
 __device__ __forceinline__ bool mbar_wait_relaxed(uint32_t bar, uint32_t parity, volatile int* abort_flag, int* status)
 {
-    if (mbar_try(bar, parity)) return true;
-    const long long t0 = clock64();
-    while (true) {
-        __nanosleep(200);
-        if (mbar_try(bar, parity)) return true;
-        if (*abort_flag) return false;
-        if (clock64() - t0 > (1ll << 31)) {
-            *abort_flag = 1;
-            atomicCAS(status, 0, 1);
-            return false;
-        }
-    }
+    return mbar_wait(bar, parity, abort_flag, status);
 }
 // one lane of a converged warp (elect.sync): the compiler then knows the branch is single-threaded and keeps
 // tcgen05 / TMA operands in uniform registers instead of emitting a per-lane waterfall loop
@@ -252,26 +250,22 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 // tansig_scaled (device_math.cuh) on W independent arguments, written stage by stage so that the W dependency
 // chains are interleaved in the instruction stream (the epilogue has only four warps per scheduler: the FP64
 // latency has to be covered by instruction-level parallelism).
+// |zs| < I8_Z_MAX is guaranteed by the host (pack_i8 bounds the pre-activations of every layer from the weights and
+// refuses the engine otherwise), so -|zs| needs no clamp and enters the FP64 pipe through operand modifiers.
+#define I8_Z_MAX 960.0
 template <int W>
 __device__ __forceinline__ void tansig_scaled_vec(const double (&zs)[W], double (&out)[W], const double* __restrict__ T)
 {
     const double A1 = 0.6931471805599453094, A2 = 0.2402265069591007123, A3 = 0.0555041086648215800,
                  A4 = 0.0096181291076284772;
     const double MAGIC = 26388279066624.0;  // 1.5 * 2^44: ulp = 2^-8
-    int sgn[W], idx[W];
-    double w[W], s[W], q[W], t[W], d[W], y0[W];
+    int idx[W];
+    double s[W], q[W], t[W], d[W], y0[W];
 #pragma unroll
     for (int i = 0; i < W; ++i) {
-        const uint32_t hi = (uint32_t)__double2hiint(zs[i]);
-        sgn[i] = (int)(hi & 0x80000000u);
-        // -|z|, clamped at -1000 on the high word (negative doubles order like unsigned integers)
-        w[i] = __hiloint2double((int)min(hi | 0x80000000u, 0xC08F4000u), __double2loint(zs[i]));
-    }
-#pragma unroll
-    for (int i = 0; i < W; ++i) {
-        const double kf = w[i] + MAGIC;
+        const double kf = MAGIC - fabs(zs[i]);
         idx[i] = __double2loint(kf);
-        s[i] = w[i] - (kf - MAGIC);
+        s[i] = (MAGIC - kf) - fabs(zs[i]);            // -|z| - rint(-|z| 2^8) 2^-8
     }
 #pragma unroll
     for (int i = 0; i < W; ++i) q[i] = fma(A4, s[i], A3);
@@ -285,7 +279,7 @@ __device__ __forceinline__ void tansig_scaled_vec(const double (&zs)[W], double 
     for (int i = 0; i < W; ++i) {
         const double Tj = T[idx[i] & 255];
         const double t0 = fma(Tj, q[i], Tj);
-        t[i] = __hiloint2double(__double2hiint(t0) + ((idx[i] >> 8) << 20), __double2loint(t0));
+        t[i] = __hiloint2double(__double2hiint(t0) + (int)((uint32_t)(idx[i] & ~255) << 12), __double2loint(t0));
     }
 #pragma unroll
     for (int i = 0; i < W; ++i) {
@@ -300,8 +294,8 @@ __device__ __forceinline__ void tansig_scaled_vec(const double (&zs)[W], double 
 #pragma unroll
     for (int i = 0; i < W; ++i) {
         const double y = fma(y0[i], q[i], y0[i]);
-        const double r = fma(2.0, y, -1.0);
-        out[i] = __hiloint2double(__double2hiint(r) ^ (sgn[i] ^ 0x80000000), __double2loint(r));
+        const double r = fma(2.0, y, -1.0);      // in [0, 1): tanh(|n|); the result takes the sign of n = -zs / (2 log2 e)
+        out[i] = __hiloint2double(__double2hiint(r) ^ (~__double2hiint(zs[i]) & (int)0x80000000), __double2loint(r));
     }
 }
 
@@ -329,18 +323,32 @@ __device__ __forceinline__ uint32_t i8_pack4(unsigned long long u0, unsigned lon
     return __byte_perm(t01, t23, 0x5410);
 }
 
-// digit words of four fixed-point values, slice by slice: w[s] holds digit (NS - 1 - s) of u0..u3 (slice 0 = most significant)
+// digit words of four fixed-point values, slice by slice: w[s] holds digit (NS - 1 - s) of u0..u3 (slice 0 = most
+// significant).  Two 4 x 4 byte transposes (PRMT butterflies): 8 + 7 operations for 7 digits instead of 21.
 template <int NS>
 __device__ __forceinline__ void i8_pack_slices(unsigned long long u0, unsigned long long u1, unsigned long long u2, unsigned long long u3,
                                                uint32_t (&w)[NS])
 {
-    if constexpr (NS > 0) w[NS - 1] = i8_pack4<0>(u0, u1, u2, u3);
-    if constexpr (NS > 1) w[NS - 2] = i8_pack4<1>(u0, u1, u2, u3);
-    if constexpr (NS > 2) w[NS - 3] = i8_pack4<2>(u0, u1, u2, u3);
-    if constexpr (NS > 3) w[NS - 4] = i8_pack4<3>(u0, u1, u2, u3);
-    if constexpr (NS > 4) w[NS - 5] = i8_pack4<4>(u0, u1, u2, u3);
-    if constexpr (NS > 5) w[NS - 6] = i8_pack4<5>(u0, u1, u2, u3);
-    if constexpr (NS > 6) w[NS - 7] = i8_pack4<6>(u0, u1, u2, u3);
+    static_assert(NS >= 4 && NS <= 7, "digits 0..3 come from the low words, 4..NS-1 from the high words");
+    {
+        const uint32_t x0 = (uint32_t)u0, x1 = (uint32_t)u1, x2 = (uint32_t)u2, x3 = (uint32_t)u3;
+        const uint32_t a01 = __byte_perm(x0, x1, 0x5140), b01 = __byte_perm(x0, x1, 0x7362);   // bytes (0,1) / (2,3) of x0, x1 interleaved
+        const uint32_t a23 = __byte_perm(x2, x3, 0x5140), b23 = __byte_perm(x2, x3, 0x7362);
+        w[NS - 1] = __byte_perm(a01, a23, 0x5410);
+        w[NS - 2] = __byte_perm(a01, a23, 0x7632);
+        w[NS - 3] = __byte_perm(b01, b23, 0x5410);
+        w[NS - 4] = __byte_perm(b01, b23, 0x7632);
+    }
+    if constexpr (NS > 4) {
+        const uint32_t x0 = (uint32_t)(u0 >> 32), x1 = (uint32_t)(u1 >> 32), x2 = (uint32_t)(u2 >> 32), x3 = (uint32_t)(u3 >> 32);
+        const uint32_t a01 = __byte_perm(x0, x1, 0x5140), a23 = __byte_perm(x2, x3, 0x5140);
+        w[NS - 5] = __byte_perm(a01, a23, 0x5410);
+        if constexpr (NS > 5) w[NS - 6] = __byte_perm(a01, a23, 0x7632);
+        if constexpr (NS > 6) {
+            const uint32_t b01 = __byte_perm(x0, x1, 0x7362), b23 = __byte_perm(x2, x3, 0x7362);
+            w[NS - 7] = __byte_perm(b01, b23, 0x5410);
+        }
+    }
 }
 
 // Write one row (candidate) of a layer-0 tile image: NIN mapminmax'ed inputs -> NS slices x 32 digit bytes, plus aux.
@@ -828,10 +836,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
 #pragma unroll
                         for (int j = 0; j < 16; ++j) a.dbg_z[(tile * I8_M + row) * 64 + cq * 16 + j] = z[j];
                     }
-                    // Phase 2: tansig, four neurons at a time; the activations are re-sliced and stored as soon as two
-                    // groups (8 digit bytes per slice) are ready, or fed to the linear output layer
+                    // Phase 2: tansig, four neurons at a time; the activations are re-sliced and stored when all four groups
+                    // (16 digit bytes per slice) are ready, or fed to the linear output layer
                     uint8_t* abuf = sm + L::OFF_A + ln * G::AH_BYTES + cq * (I8_M * 16) + row * 16;
-                    uint32_t keep[NS];
+                    constexpr bool WIDE_STORE = (NS <= 4);   // 7 digits: three groups of pending words would spill (measured: +6 % step time)
+                    uint32_t keep[WIDE_STORE ? 3 : 1][NS];
                     double part = 0.0;
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
@@ -845,13 +854,27 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                             for (int i = 0; i < 4; ++i) u[i] = i8_quantize(act[i], G::SCALE_H);
                             uint32_t w[NS];
                             i8_pack_slices<NS>(u[0], u[1], u[2], u[3], w);      // w[s]: slice s (0 = most significant)
-                            if ((g & 1) == 0) {
+                            // the warp owns 16 neurons = one 16-byte row of the K-major core matrices.  4 digits: ONE 16-byte store per
+                            // slice (4 wavefronts for the 512 contiguous bytes of the warp, no bank conflict), the digit words wait
+                            // in the registers the z values leave; 7 digits: 8-byte stores after every second group
+                            if constexpr (WIDE_STORE) {
+                                if (g < 3) {
 #pragma unroll
-                                for (int b = 0; b < NS; ++b) keep[b] = w[b];
+                                    for (int b = 0; b < NS; ++b) keep[g][b] = w[b];
+                                } else {
+#pragma unroll
+                                    for (int b = 0; b < NS; ++b)
+                                        *reinterpret_cast<uint4*>(abuf + b * (I8_M * 64)) = make_uint4(keep[0][b], keep[1][b], keep[2][b], w[b]);
+                                }
                             } else {
+                                if ((g & 1) == 0) {
 #pragma unroll
-                                for (int b = 0; b < NS; ++b)
-                                    *reinterpret_cast<uint2*>(abuf + b * (I8_M * 64) + (g >> 1) * 8) = make_uint2(keep[b], w[b]);
+                                    for (int b = 0; b < NS; ++b) keep[0][b] = w[b];
+                                } else {
+#pragma unroll
+                                    for (int b = 0; b < NS; ++b)
+                                        *reinterpret_cast<uint2*>(abuf + b * (I8_M * 64) + (g >> 1) * 8) = make_uint2(keep[0][b], w[b]);
+                                }
                             }
                         } else {
 #pragma unroll
