@@ -351,6 +351,94 @@ __device__ __forceinline__ void i8_pack_slices(unsigned long long u0, unsigned l
     }
 }
 
+// tansig of four pre-activations (as tansig_scaled_vec<4>) with the re-slicing of the PREVIOUS four activations woven into
+// it, stage by stage.  The four epilogue warps of an SM sub-partition run in lock-step (they wait for the same
+// accumulators), so a stretch of pure FP64 work in the instruction stream saturates the FP64 pipe (one warp instruction
+// every two clocks) while the integer pipes idle, and a stretch of pure byte shuffling does the opposite: measured step
+// time was the SUM of the two.  Interleaved, the integer work issues in the shadow of the FP64 pipe.
+template <int NS, bool SLICE_PREV>
+__device__ __forceinline__ void tansig4_slice4(const double (&zs)[4], double (&out)[4], const double* __restrict__ T, const double (&prev)[4],
+                                               double scale, uint32_t (&w)[NS])
+{
+    const double A1 = 0.6931471805599453094, A2 = 0.2402265069591007123, A3 = 0.0555041086648215800,
+                 A4 = 0.0096181291076284772;
+    const double MAGIC = 26388279066624.0;  // 1.5 * 2^44: ulp = 2^-8
+    int idx[4];
+    double s[4], q[4], t[4], d[4], y0[4], qd[4];
+    uint32_t lo[4], hi[4], a01, a23, b01, b23;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double kf = MAGIC - fabs(zs[i]);
+        idx[i] = __double2loint(kf);
+        s[i] = (MAGIC - kf) - fabs(zs[i]);
+    }
+    if constexpr (SLICE_PREV) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) qd[i] = fma(prev[i], scale, I8_MAGIC52);          // i8_quantize, first half
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = fma(A4, s[i], A3);
+    if constexpr (SLICE_PREV) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                                                   // (bits - magic) << 3 as two words
+            const uint32_t l32 = (uint32_t)__double2loint(qd[i]), h32 = (uint32_t)__double2hiint(qd[i]) - 0x43380000u;
+            lo[i] = l32 << 3;
+            hi[i] = __funnelshift_l(l32, h32, 3);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = fma(q[i], s[i], A2);
+    if constexpr (SLICE_PREV) {
+        a01 = __byte_perm(lo[0], lo[1], 0x5140); b01 = __byte_perm(lo[0], lo[1], 0x7362);
+        a23 = __byte_perm(lo[2], lo[3], 0x5140); b23 = __byte_perm(lo[2], lo[3], 0x7362);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = fma(q[i], s[i], A1);
+    if constexpr (SLICE_PREV) {
+        w[NS - 1] = __byte_perm(a01, a23, 0x5410);
+        w[NS - 2] = __byte_perm(a01, a23, 0x7632);
+        w[NS - 3] = __byte_perm(b01, b23, 0x5410);
+        w[NS - 4] = __byte_perm(b01, b23, 0x7632);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = q[i] * s[i];
+    if constexpr (SLICE_PREV && NS > 4) {
+        a01 = __byte_perm(hi[0], hi[1], 0x5140);
+        a23 = __byte_perm(hi[2], hi[3], 0x5140);
+        if constexpr (NS > 6) {
+            b01 = __byte_perm(hi[0], hi[1], 0x7362);
+            b23 = __byte_perm(hi[2], hi[3], 0x7362);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double Tj = T[idx[i] & 255];
+        const double t0 = fma(Tj, q[i], Tj);
+        t[i] = __hiloint2double(__double2hiint(t0) + (int)((uint32_t)(idx[i] & ~255) << 12), __double2loint(t0));
+    }
+    if constexpr (SLICE_PREV && NS > 4) {
+        w[NS - 5] = __byte_perm(a01, a23, 0x5410);
+        if constexpr (NS > 5) w[NS - 6] = __byte_perm(a01, a23, 0x7632);
+        if constexpr (NS > 6) w[NS - 7] = __byte_perm(b01, b23, 0x5410);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        d[i] = 1.0 + t[i];
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0[i]) : "d"(d[i]));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double e = fma(-d[i], y0[i], 1.0);
+        q[i] = fma(e, e, e);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double y = fma(y0[i], q[i], y0[i]);
+        const double r = fma(2.0, y, -1.0);
+        out[i] = __hiloint2double(__double2hiint(r) ^ (~__double2hiint(zs[i]) & (int)0x80000000), __double2loint(r));
+    }
+}
+
 // Write one row (candidate) of a layer-0 tile image: NIN mapminmax'ed inputs -> NS slices x 32 digit bytes, plus aux.
 // Shared-memory image: [slice s (0 = most significant)][k chunk c = k / 16][row][k % 16]; staged tile: see I8Dig::TILE_BYTES.
 template <int NIN, int NS>
@@ -836,47 +924,64 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
 #pragma unroll
                         for (int j = 0; j < 16; ++j) a.dbg_z[(tile * I8_M + row) * 64 + cq * 16 + j] = z[j];
                     }
-                    // Phase 2: tansig, four neurons at a time; the activations are re-sliced and stored when all four groups
-                    // (16 digit bytes per slice) are ready, or fed to the linear output layer
+                    // Phase 2: tansig, four neurons at a time; the activations are re-sliced and stored, or fed to the linear output layer
                     uint8_t* abuf = sm + L::OFF_A + ln * G::AH_BYTES + cq * (I8_M * 16) + row * 16;
                     constexpr bool WIDE_STORE = (NS <= 4);   // 7 digits: three groups of pending words would spill (measured: +6 % step time)
-                    uint32_t keep[WIDE_STORE ? 3 : 1][NS];
                     double part = 0.0;
+                    if (l < NHID - 1) {
+                        // software pipeline over the four groups: tansig of group g runs interleaved with the re-slicing of group
+                        // g - 1 (tansig4_slice4).  The warp owns 16 neurons = one 16-byte row of the K-major core matrices.  4 digits:
+                        // ONE 16-byte store per slice (no bank conflict), the digit words wait in the registers the z values leave;
+                        // 7 digits: 8-byte stores after every second group
+                        uint32_t keep[WIDE_STORE ? 3 : 1][NS], w[NS];
+                        double act[2][4];
+                        {
+                            double zz[4];
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        double zz[4], act[4];
+                            for (int i = 0; i < 4; ++i) zz[i] = z[i];
+                            tansig4_slice4<NS, false>(zz, act[0], tab, act[0], G::SCALE_H, w);
+                        }
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) zz[i] = z[g * 4 + i];
-                        tansig_scaled_vec<4>(zz, act, tab);
-                        if (l < NHID - 1) {
-                            unsigned long long u[4];
+                        for (int g = 1; g <= 4; ++g) {
+                            if (g < 4) {
+                                double zz[4];
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) u[i] = i8_quantize(act[i], G::SCALE_H);
-                            uint32_t w[NS];
-                            i8_pack_slices<NS>(u[0], u[1], u[2], u[3], w);      // w[s]: slice s (0 = most significant)
-                            // the warp owns 16 neurons = one 16-byte row of the K-major core matrices.  4 digits: ONE 16-byte store per
-                            // slice (4 wavefronts for the 512 contiguous bytes of the warp, no bank conflict), the digit words wait
-                            // in the registers the z values leave; 7 digits: 8-byte stores after every second group
+                                for (int i = 0; i < 4; ++i) zz[i] = z[g * 4 + i];
+                                tansig4_slice4<NS, true>(zz, act[g & 1], tab, act[(g - 1) & 1], G::SCALE_H, w);
+                            } else {
+                                unsigned long long u[4];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) u[i] = i8_quantize(act[1][i], G::SCALE_H);
+                                i8_pack_slices<NS>(u[0], u[1], u[2], u[3], w);
+                            }
+                            const int gp = g - 1;                                  // w: digit words of group gp, w[s] = slice s (0 = most significant)
                             if constexpr (WIDE_STORE) {
-                                if (g < 3) {
+                                if (gp < 3) {
 #pragma unroll
-                                    for (int b = 0; b < NS; ++b) keep[g][b] = w[b];
+                                    for (int b = 0; b < NS; ++b) keep[gp][b] = w[b];
                                 } else {
 #pragma unroll
                                     for (int b = 0; b < NS; ++b)
                                         *reinterpret_cast<uint4*>(abuf + b * (I8_M * 64)) = make_uint4(keep[0][b], keep[1][b], keep[2][b], w[b]);
                                 }
                             } else {
-                                if ((g & 1) == 0) {
+                                if ((gp & 1) == 0) {
 #pragma unroll
                                     for (int b = 0; b < NS; ++b) keep[0][b] = w[b];
                                 } else {
 #pragma unroll
                                     for (int b = 0; b < NS; ++b)
-                                        *reinterpret_cast<uint2*>(abuf + b * (I8_M * 64) + (g >> 1) * 8) = make_uint2(keep[0][b], w[b]);
+                                        *reinterpret_cast<uint2*>(abuf + b * (I8_M * 64) + (gp >> 1) * 8) = make_uint2(keep[0][b], w[b]);
                                 }
                             }
-                        } else {
+                        }
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            double zz[4], act[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) zz[i] = z[g * 4 + i];
+                            tansig_scaled_vec<4>(zz, act, tab);
 #pragma unroll
                             for (int i = 0; i < 4; ++i) part = fma(wout[g * 4 + i], act[i], part);
                         }
