@@ -318,7 +318,39 @@ def _dropin_rounds(name, reps):
         out["strat%d" % strat] = dict(sdp_cuts=int(nb), tri_cuts=int(nt), degenerate=int(rl.degenerate),
                                       **{nm + "_ms": float(np.median(v)) for nm, v in ph.items()})
         out["strat%d" % strat]["subsets_per_s"] = N / (out["strat%d" % strat]["select_ms"] * 1e-3)
+        # the same rounds with an LP sink that takes the rows as CSR arrays (linear_constraints.add_rows_csr: a thin CPXaddrows
+        # wrapper): no per-row SparsePair objects -- what is left is the selection call and the C ABI
+        sink, keep = _CsrSink(), cs._my_prob.linear_constraints
+        cs._my_prob.linear_constraints = sink
+        try:
+            ts = []
+            for rep, vv in enumerate(points):
+                sink.blocks = []
+                t0 = time.perf_counter()
+                r = cs._sel_eigcut_by_ordering_on_measure(strat, vv, 1, sel_size=k)
+                cs._gen_eigcuts_selected(strat, k, r[1] if strat == 4 else r, vars_values=vv)
+                if wl.get("triangles"):
+                    cs._CutSolver__separate_and_add_triangle(0.1, vv)
+                if rep:
+                    ts.append((time.perf_counter() - t0) * 1e3)
+            out["strat%d" % strat]["round_csr_sink_ms"] = float(np.median(ts))
+            out["strat%d" % strat]["rows_csr_sink"] = int(sum(len(b[3]) for b in sink.blocks))
+        finally:
+            cs._my_prob.linear_constraints = keep
     return out
+
+
+class _CsrSink(object):
+    """LP row sink with the one-shot CSR entry point the drop-in looks for (cut_select_qp._add_rows_csr)."""
+
+    def __init__(self):
+        self.blocks, self.rows = [], []
+
+    def add_rows_csr(self, rowptr, ind, val, rhs, senses):
+        self.blocks.append((rowptr, ind, val, rhs, senses))
+
+    def add(self, lin_expr=None, rhs=None, senses=None, **kw):
+        self.rows.extend(zip(lin_expr, rhs, senses))
 
 
 PUBLISHED_SEP = {"cfg2": "reference separation time per round on spar125-075-1 (data_tables/data_all_boxqp_4rounds.csv:100): "

@@ -784,16 +784,27 @@ static int ensure_tiles(sdpcs_ctx* ctx, i64 n_tiles, i64 tile_bytes = I8_TILE_BY
     return SDPCS_OK;
 }
 
-template <int NHID, int D, int NS = I8_NS>
-static int launch_mlp_i8(sdpcs_ctx* ctx, const MlpI8Args& m)
+template <int NHID, int D, int NS, bool DBG>
+static int launch_mlp_i8_inst(sdpcs_ctx* ctx, const MlpI8Args& m)
 {
     using L = I8Smem<NHID, NS>;
-    auto kern = k_mlp_i8<NHID, D, NS>;
+    auto kern = k_mlp_i8<NHID, D, NS, DBG>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     const unsigned grid = (unsigned)std::max<i64>(1, std::min<i64>(m.n_tiles, ctx->sms));
     kern<<<grid, I8_THREADS, L::TOTAL, ctx->stream>>>(m);
     CU(cudaGetLastError());
     return SDPCS_OK;
+}
+
+// the variant that can dump the pre-activations of a layer (sdpcs_nn_debug_layer) is a separate instance: the product
+// kernel carries no debug branch
+template <int NHID, int D, int NS = I8_NS>
+static int launch_mlp_i8(sdpcs_ctx* ctx, const MlpI8Args& m)
+{
+    if constexpr (D == 0) {
+        if (m.dbg_z) return launch_mlp_i8_inst<NHID, D, NS, true>(ctx, m);
+    }
+    return launch_mlp_i8_inst<NHID, D, NS, false>(ctx, m);
 }
 
 // optimality measure of the N candidates described by `a` through the tcgen05 int8-sliced MLP, layer-0 digit images

@@ -25,6 +25,7 @@
 //                                   into the next layer's A operand in shared memory (UMMA canonical K-major layout)
 //   While the epilogue warps work on tile X, the tensor core runs the next layer of tile Y.
 #pragma once
+#include <type_traits>
 #include "score_kernels.cuh"
 
 namespace sdpcs {
@@ -147,6 +148,11 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive by lane 0 of a converged warp as a predicated instruction (no branch: the step stays one basic block for ptxas)
+__device__ __forceinline__ void mbar_arrive_lane0(uint32_t bar, int lane)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, 0;\n\t@p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" ::"r"(bar), "r"(lane) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
@@ -351,76 +357,47 @@ __device__ __forceinline__ void i8_pack_slices(unsigned long long u0, unsigned l
     }
 }
 
-// tansig of four pre-activations (as tansig_scaled_vec<4>) with the re-slicing of the PREVIOUS four activations woven into
-// it, stage by stage.  The four epilogue warps of an SM sub-partition run in lock-step (they wait for the same
-// accumulators), so a stretch of pure FP64 work in the instruction stream saturates the FP64 pipe (one warp instruction
-// every two clocks) while the integer pipes idle, and a stretch of pure byte shuffling does the opposite: measured step
-// time was the SUM of the two.  Interleaved, the integer work issues in the shadow of the FP64 pipe.
-template <int NS, bool SLICE_PREV>
-__device__ __forceinline__ void tansig4_slice4(const double (&zs)[4], double (&out)[4], const double* __restrict__ T, const double (&prev)[4],
-                                               double scale, uint32_t (&w)[NS])
+// tansig of four pre-activations (as tansig_scaled_vec<4>) with independent "side work" woven into it, stage by stage:
+// side(integral_constant<int, k>), k = 0..5, is called between the stages.  The four epilogue warps of an SM sub-partition
+// run in lock-step (they wait for the same accumulators), so a stretch of pure FP64 work in the instruction stream
+// saturates the FP64 pipe (one warp instruction every two clocks) while the integer pipes idle, and a stretch of pure
+// integer work does the opposite: measured step time was the SUM of the two.  Woven, the integer work (re-slicing of the
+// previous four activations, recombination of the next accumulators) issues in the shadow of the FP64 pipe.
+template <int K> using i8_stage = std::integral_constant<int, K>;
+template <class Side>
+__device__ __forceinline__ void tansig4_woven(const double (&zs)[4], double (&out)[4], const double* __restrict__ T, Side&& side)
 {
     const double A1 = 0.6931471805599453094, A2 = 0.2402265069591007123, A3 = 0.0555041086648215800,
                  A4 = 0.0096181291076284772;
     const double MAGIC = 26388279066624.0;  // 1.5 * 2^44: ulp = 2^-8
     int idx[4];
-    double s[4], q[4], t[4], d[4], y0[4], qd[4];
-    uint32_t lo[4], hi[4], a01, a23, b01, b23;
+    double s[4], q[4], t[4], d[4], y0[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const double kf = MAGIC - fabs(zs[i]);
         idx[i] = __double2loint(kf);
         s[i] = (MAGIC - kf) - fabs(zs[i]);
     }
-    if constexpr (SLICE_PREV) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) qd[i] = fma(prev[i], scale, I8_MAGIC52);          // i8_quantize, first half
-    }
+    side(i8_stage<0>{});
 #pragma unroll
     for (int i = 0; i < 4; ++i) q[i] = fma(A4, s[i], A3);
-    if constexpr (SLICE_PREV) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {                                                   // (bits - magic) << 3 as two words
-            const uint32_t l32 = (uint32_t)__double2loint(qd[i]), h32 = (uint32_t)__double2hiint(qd[i]) - 0x43380000u;
-            lo[i] = l32 << 3;
-            hi[i] = __funnelshift_l(l32, h32, 3);
-        }
-    }
+    side(i8_stage<1>{});
 #pragma unroll
     for (int i = 0; i < 4; ++i) q[i] = fma(q[i], s[i], A2);
-    if constexpr (SLICE_PREV) {
-        a01 = __byte_perm(lo[0], lo[1], 0x5140); b01 = __byte_perm(lo[0], lo[1], 0x7362);
-        a23 = __byte_perm(lo[2], lo[3], 0x5140); b23 = __byte_perm(lo[2], lo[3], 0x7362);
-    }
+    side(i8_stage<2>{});
 #pragma unroll
     for (int i = 0; i < 4; ++i) q[i] = fma(q[i], s[i], A1);
-    if constexpr (SLICE_PREV) {
-        w[NS - 1] = __byte_perm(a01, a23, 0x5410);
-        w[NS - 2] = __byte_perm(a01, a23, 0x7632);
-        w[NS - 3] = __byte_perm(b01, b23, 0x5410);
-        w[NS - 4] = __byte_perm(b01, b23, 0x7632);
-    }
+    side(i8_stage<3>{});
 #pragma unroll
     for (int i = 0; i < 4; ++i) q[i] = q[i] * s[i];
-    if constexpr (SLICE_PREV && NS > 4) {
-        a01 = __byte_perm(hi[0], hi[1], 0x5140);
-        a23 = __byte_perm(hi[2], hi[3], 0x5140);
-        if constexpr (NS > 6) {
-            b01 = __byte_perm(hi[0], hi[1], 0x7362);
-            b23 = __byte_perm(hi[2], hi[3], 0x7362);
-        }
-    }
+    side(i8_stage<4>{});
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const double Tj = T[idx[i] & 255];
         const double t0 = fma(Tj, q[i], Tj);
         t[i] = __hiloint2double(__double2hiint(t0) + (int)((uint32_t)(idx[i] & ~255) << 12), __double2loint(t0));
     }
-    if constexpr (SLICE_PREV && NS > 4) {
-        w[NS - 5] = __byte_perm(a01, a23, 0x5410);
-        if constexpr (NS > 5) w[NS - 6] = __byte_perm(a01, a23, 0x7632);
-        if constexpr (NS > 6) w[NS - 7] = __byte_perm(b01, b23, 0x5410);
-    }
+    side(i8_stage<5>{});
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         d[i] = 1.0 + t[i];
@@ -438,6 +415,98 @@ __device__ __forceinline__ void tansig4_slice4(const double (&zs)[4], double (&o
         out[i] = __hiloint2double(__double2hiint(r) ^ (~__double2hiint(zs[i]) & (int)0x80000000), __double2loint(r));
     }
 }
+
+// side work: digit slicing of four activations (i8_quantize + i8_pack_slices), cut into the six stages of tansig4_woven
+template <int NS>
+struct I8SliceSide {
+    const double (&prev)[4];
+    double scale;
+    uint32_t (&w)[NS];
+    double qd[4];
+    uint32_t lo[4], hi[4], a01, a23, b01, b23;
+    __device__ __forceinline__ I8SliceSide(const double (&p)[4], double sc, uint32_t (&ww)[NS]) : prev(p), scale(sc), w(ww) {}
+    template <int K>
+    __device__ __forceinline__ void operator()(i8_stage<K>)
+    {
+        if constexpr (K == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) qd[i] = fma(prev[i], scale, I8_MAGIC52);
+        } else if constexpr (K == 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {                                               // (bits - magic) << 3 as two words
+                const uint32_t l32 = (uint32_t)__double2loint(qd[i]), h32 = (uint32_t)__double2hiint(qd[i]) - 0x43380000u;
+                lo[i] = l32 << 3;
+                hi[i] = __funnelshift_l(l32, h32, 3);
+            }
+        } else if constexpr (K == 2) {
+            a01 = __byte_perm(lo[0], lo[1], 0x5140); b01 = __byte_perm(lo[0], lo[1], 0x7362);
+            a23 = __byte_perm(lo[2], lo[3], 0x5140); b23 = __byte_perm(lo[2], lo[3], 0x7362);
+        } else if constexpr (K == 3) {
+            w[NS - 1] = __byte_perm(a01, a23, 0x5410);
+            w[NS - 2] = __byte_perm(a01, a23, 0x7632);
+            w[NS - 3] = __byte_perm(b01, b23, 0x5410);
+            w[NS - 4] = __byte_perm(b01, b23, 0x7632);
+        } else if constexpr (K == 4) {
+            if constexpr (NS > 4) {
+                a01 = __byte_perm(hi[0], hi[1], 0x5140);
+                a23 = __byte_perm(hi[2], hi[3], 0x5140);
+                if constexpr (NS > 6) {
+                    b01 = __byte_perm(hi[0], hi[1], 0x7362);
+                    b23 = __byte_perm(hi[2], hi[3], 0x7362);
+                }
+            }
+        } else {
+            if constexpr (NS > 4) w[NS - 5] = __byte_perm(a01, a23, 0x5410);
+            if constexpr (NS > 5) w[NS - 6] = __byte_perm(a01, a23, 0x7632);
+            if constexpr (NS > 6) w[NS - 7] = __byte_perm(b01, b23, 0x5410);
+        }
+    }
+};
+struct I8NoSide {
+    template <int K>
+    __device__ __forceinline__ void operator()(i8_stage<K>) {}
+};
+
+// exact recombination of the NS diagonals of one output: value = sum_d S_d 256^(NS-1-d) as exact integers, pre-biased so that
+// the bit pattern is the double 1.5 * 2^52 + acc; one rounding; z = -2 log2(e) * (W a + b)
+template <int NS>
+__device__ __forceinline__ double i8_recombine(const uint32_t (&v)[NS][8], int j, double2 cb)
+{
+    double val;
+    if constexpr (NS == 7) {
+        long long accH = I8_MAGIC52_BITS, accL = I8_MAGIC52_BITS;
+        accH = (long long)(int)v[0][j] * 65536ll + accH;
+        accH = (long long)(int)v[1][j] * 256ll + accH;
+        accH = (long long)(int)v[2][j] * 1ll + accH;
+        accL = (long long)(int)v[3][j] * 16777216ll + accL;
+        accL = (long long)(int)v[4][j] * 65536ll + accL;
+        accL = (long long)(int)v[5][j] * 256ll + accL;
+        accL = (long long)(int)v[6][j] * 1ll + accL;
+        const double dl = __longlong_as_double(accL) - I8_MAGIC52;
+        const double dh = __longlong_as_double(accH) - I8_MAGIC52;
+        val = fma(dh, 4294967296.0, dl);
+    } else {
+        static_assert(NS == 7 || NS <= 4, "recombination written for 7 and for <= 4 digits");
+        long long acc = I8_MAGIC52_BITS;           // |sum| < 2^(24 + 8 (NS - 1)) <= 2^48
+#pragma unroll
+        for (int dg = 0; dg < NS; ++dg) acc = (long long)(int)v[dg][j] * (1ll << (8 * (NS - 1 - dg))) + acc;
+        val = __longlong_as_double(acc) - I8_MAGIC52;
+    }
+    return fma(val, cb.x, cb.y);
+}
+// side work: recombination of outputs 4..7 of the second batch of TMEM loads (z[12..15]), one per stage
+template <int NS>
+struct I8RecombineSide {
+    const uint32_t (&v)[NS][8];
+    const double2* csbs;
+    double (&z)[16];
+    __device__ __forceinline__ I8RecombineSide(const uint32_t (&vv)[NS][8], const double2* c, double (&zz)[16]) : v(vv), csbs(c), z(zz) {}
+    template <int K>
+    __device__ __forceinline__ void operator()(i8_stage<K>)
+    {
+        if constexpr (K < 4) z[12 + K] = i8_recombine<NS>(v, 4 + K, csbs[12 + K]);
+    }
+};
 
 // Write one row (candidate) of a layer-0 tile image: NIN mapminmax'ed inputs -> NS slices x 32 digit bytes, plus aux.
 // Shared-memory image: [slice s (0 = most significant)][k chunk c = k / 16][row][k % 16]; staged tile: see I8Dig::TILE_BYTES.
@@ -650,7 +719,7 @@ __device__ __forceinline__ void i8_prep_row_smem(const ScoreArgs& a, const int (
 // ---------------------------------------------------------------------------------------------------
 // D > 0: candidates come from the instance (the producer warp builds the layer-0 image in shared memory);
 // D = 0: raw network inputs, layer-0 images prepared by k_prep_i8_raw and loaded by TMA (sdpcs_nn_eval).
-template <int NHID, int D, int NS = I8_NS>
+template <int NHID, int D, int NS = I8_NS, bool DBG = false>
 __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
 {
     using L = I8Smem<NHID, NS>;
@@ -876,116 +945,101 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
 #endif
                     const double2* csbs = reinterpret_cast<const double2*>(par + L::P_CS) + l * 64 + cq * 16;   // (cs, bs) pairs
                     const double* wout = par + L::P_WOUT + cq * 16;
-                    // Phase 1: read the NS diagonals (two batches of TMEM loads, 8 neurons each), recombine them exactly in
-                    // int64 and reduce to the FP64 pre-activations.  The accumulator stage is handed back to the MMA issuer
-                    // as soon as the second batch is in registers.
-                    double z[16];
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        uint32_t v[NS][8];
-#pragma unroll
-                        for (int dg = 0; dg < NS; ++dg) tmem_ld8_async(tbase + dg * I8_N + half * 8, v[dg]);
-                        tmem_wait_ld();
-                        if (half == 1) {
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(B_EMPTY + 8 * st);
-                            I8_STAMP(step, 2);
-                        }
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            // value = sum_d S_d 256^(NS-1-d): exact integers, pre-biased so that the bit pattern is the double
-                            // 1.5 * 2^52 + acc; one rounding; z = -2 log2(e) * (W a + b)
-                            double val;
-                            if constexpr (NS == 7) {
-                                long long accH = I8_MAGIC52_BITS, accL = I8_MAGIC52_BITS;
-                                accH = (long long)(int)v[0][j] * 65536ll + accH;
-                                accH = (long long)(int)v[1][j] * 256ll + accH;
-                                accH = (long long)(int)v[2][j] * 1ll + accH;
-                                accL = (long long)(int)v[3][j] * 16777216ll + accL;
-                                accL = (long long)(int)v[4][j] * 65536ll + accL;
-                                accL = (long long)(int)v[5][j] * 256ll + accL;
-                                accL = (long long)(int)v[6][j] * 1ll + accL;
-                                const double dl = __longlong_as_double(accL) - I8_MAGIC52;
-                                const double dh = __longlong_as_double(accH) - I8_MAGIC52;
-                                val = fma(dh, 4294967296.0, dl);
-                            } else {
-                                static_assert(NS == 7 || NS <= 4, "recombination written for 7 and for <= 4 digits");
-                                long long acc = I8_MAGIC52_BITS;           // |sum| < 2^(24 + 8 (NS - 1)) <= 2^48
-#pragma unroll
-                                for (int dg = 0; dg < NS; ++dg) acc = (long long)(int)v[dg][j] * (1ll << (8 * (NS - 1 - dg))) + acc;
-                                val = __longlong_as_double(acc) - I8_MAGIC52;
-                            }
-                            const double2 cb = csbs[half * 8 + j];
-                            z[half * 8 + j] = fma(val, cb.x, cb.y);
-                        }
-                    }
-                    if (a.dbg_z && l == a.dbg_layer) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) a.dbg_z[(tile * I8_M + row) * 64 + cq * 16 + j] = z[j];
-                    }
-                    // Phase 2: tansig, four neurons at a time; the activations are re-sliced and stored, or fed to the linear output layer
+                    // Phase 1: read the NS diagonals (two batches of TMEM loads, 8 neurons each), recombine them exactly in int64 and
+                    // reduce to the FP64 pre-activations.  The accumulator stage is handed back to the MMA issuer as soon as the
+                    // second batch is in registers.  Phase 2: tansig, four neurons at a time, as a software pipeline: the tansig of
+                    // group g is woven with the recombination of the last four outputs (g = 0) or the re-slicing of group g - 1
+                    // (tansig4_woven).  From the hand-back to the stores the step is ONE basic block (no branch on the layer
+                    // inside: hidden layers and the output layer are two instances of the body).
                     uint8_t* abuf = sm + L::OFF_A + ln * G::AH_BYTES + cq * (I8_M * 16) + row * 16;
                     constexpr bool WIDE_STORE = (NS <= 4);   // 7 digits: three groups of pending words would spill (measured: +6 % step time)
                     double part = 0.0;
-                    if (l < NHID - 1) {
-                        // software pipeline over the four groups: tansig of group g runs interleaved with the re-slicing of group
-                        // g - 1 (tansig4_slice4).  The warp owns 16 neurons = one 16-byte row of the K-major core matrices.  4 digits:
-                        // ONE 16-byte store per slice (no bank conflict), the digit words wait in the registers the z values leave;
-                        // 7 digits: 8-byte stores after every second group
-                        uint32_t keep[WIDE_STORE ? 3 : 1][NS], w[NS];
+                    auto body = [&](auto last_tag) {
+                        constexpr bool LAST = decltype(last_tag)::value;
+                        double z[16];
+                        uint32_t v[NS][8];
+#pragma unroll
+                        for (int dg = 0; dg < NS; ++dg) tmem_ld8_async(tbase + dg * I8_N, v[dg]);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) z[j] = i8_recombine<NS>(v, j, csbs[j]);
+#pragma unroll
+                        for (int dg = 0; dg < NS; ++dg) tmem_ld8_async(tbase + dg * I8_N + 8, v[dg]);
+                        tmem_wait_ld();
+                        tc_fence_before();
+                        __syncwarp();
+                        mbar_arrive_lane0(B_EMPTY + 8 * st, lane);
+                        I8_STAMP(step, 2);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) z[8 + j] = i8_recombine<NS>(v, j, csbs[8 + j]);
                         double act[2][4];
                         {
                             double zz[4];
 #pragma unroll
                             for (int i = 0; i < 4; ++i) zz[i] = z[i];
-                            tansig4_slice4<NS, false>(zz, act[0], tab, act[0], G::SCALE_H, w);
+                            tansig4_woven(zz, act[0], tab, I8RecombineSide<NS>(v, csbs, z));
                         }
+                        if constexpr (!LAST) {
+                            // The warp owns 16 neurons = one 16-byte row of the K-major core matrices.  4 digits: ONE 16-byte store per
+                            // slice (no bank conflict), the digit words wait in the registers the z values leave; 7 digits: 8-byte
+                            // stores after every second group
+                            uint32_t keep[WIDE_STORE ? 3 : 1][NS], w[NS];
 #pragma unroll
-                        for (int g = 1; g <= 4; ++g) {
-                            if (g < 4) {
+                            for (int g = 1; g <= 4; ++g) {
+                                if (g < 4) {
+                                    double zz[4];
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) zz[i] = z[g * 4 + i];
+                                    tansig4_woven(zz, act[g & 1], tab, I8SliceSide<NS>(act[(g - 1) & 1], G::SCALE_H, w));
+                                } else {
+                                    unsigned long long u[4];
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) u[i] = i8_quantize(act[1][i], G::SCALE_H);
+                                    i8_pack_slices<NS>(u[0], u[1], u[2], u[3], w);
+                                }
+                                const int gp = g - 1;                                  // w: digit words of group gp, w[s] = slice s (0 = most significant)
+                                if constexpr (WIDE_STORE) {
+                                    if (gp < 3) {
+#pragma unroll
+                                        for (int b = 0; b < NS; ++b) keep[gp][b] = w[b];
+                                    } else {
+#pragma unroll
+                                        for (int b = 0; b < NS; ++b)
+                                            *reinterpret_cast<uint4*>(abuf + b * (I8_M * 64)) = make_uint4(keep[0][b], keep[1][b], keep[2][b], w[b]);
+                                    }
+                                } else {
+                                    if ((gp & 1) == 0) {
+#pragma unroll
+                                        for (int b = 0; b < NS; ++b) keep[0][b] = w[b];
+                                    } else {
+#pragma unroll
+                                        for (int b = 0; b < NS; ++b)
+                                            *reinterpret_cast<uint2*>(abuf + b * (I8_M * 64) + (gp >> 1) * 8) = make_uint2(keep[0][b], w[b]);
+                                    }
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) part = fma(wout[i], act[0][i], part);
+#pragma unroll
+                            for (int g = 1; g < 4; ++g) {
                                 double zz[4];
 #pragma unroll
                                 for (int i = 0; i < 4; ++i) zz[i] = z[g * 4 + i];
-                                tansig4_slice4<NS, true>(zz, act[g & 1], tab, act[(g - 1) & 1], G::SCALE_H, w);
-                            } else {
-                                unsigned long long u[4];
+                                tansig4_woven(zz, act[1], tab, I8NoSide());
 #pragma unroll
-                                for (int i = 0; i < 4; ++i) u[i] = i8_quantize(act[1][i], G::SCALE_H);
-                                i8_pack_slices<NS>(u[0], u[1], u[2], u[3], w);
-                            }
-                            const int gp = g - 1;                                  // w: digit words of group gp, w[s] = slice s (0 = most significant)
-                            if constexpr (WIDE_STORE) {
-                                if (gp < 3) {
-#pragma unroll
-                                    for (int b = 0; b < NS; ++b) keep[gp][b] = w[b];
-                                } else {
-#pragma unroll
-                                    for (int b = 0; b < NS; ++b)
-                                        *reinterpret_cast<uint4*>(abuf + b * (I8_M * 64)) = make_uint4(keep[0][b], keep[1][b], keep[2][b], w[b]);
-                                }
-                            } else {
-                                if ((gp & 1) == 0) {
-#pragma unroll
-                                    for (int b = 0; b < NS; ++b) keep[0][b] = w[b];
-                                } else {
-#pragma unroll
-                                    for (int b = 0; b < NS; ++b)
-                                        *reinterpret_cast<uint2*>(abuf + b * (I8_M * 64) + (gp >> 1) * 8) = make_uint2(keep[0][b], w[b]);
-                                }
+                                for (int i = 0; i < 4; ++i) part = fma(wout[g * 4 + i], act[1][i], part);
                             }
                         }
-                    } else {
+                        if constexpr (DBG) {
+                            if (a.dbg_z && l == a.dbg_layer) {
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            double zz[4], act[4];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) zz[i] = z[g * 4 + i];
-                            tansig_scaled_vec<4>(zz, act, tab);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) part = fma(wout[g * 4 + i], act[i], part);
+                                for (int j = 0; j < 16; ++j) a.dbg_z[(tile * I8_M + row) * 64 + cq * 16 + j] = z[j];
+                            }
                         }
-                    }
+                    };
+                    if (l < NHID - 1) body(std::false_type{});
+                    else body(std::true_type{});
                     if (l < NHID - 1) {
                         fence_async_smem();
                         __syncwarp();
