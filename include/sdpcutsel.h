@@ -65,10 +65,12 @@ typedef struct sdpcs_params {
 } sdpcs_params;
 
 /* NN engines.  Both evaluate neural_net_{2..5}D (cut_select_qp.py:579-582) to FP64 accuracy:
- *   TCGEN05: error-free int8-sliced contraction on the 5th-generation tensor cores (tcgen05.mma kind::i8,
+ *   TCGEN05: FP64-accurate int8-sliced contraction on the 5th-generation tensor cores (tcgen05.mma kind::i8,
  *            accumulators in TMEM), FP64 only for bias / tansig; NN inputs must lie in (-2, 2) after mapminmax
  *            (always true for LP points in the McCormick box) -- otherwise the call transparently re-scores
- *            with the DMMA engine and counts it in sdpcs_timings.nn_fallbacks;
+ *            with the DMMA engine and counts it in sdpcs_timings.nn_fallbacks; sdpcs_set_weights bounds the
+ *            pre-activations of every layer from the weights and serves a net whose scaled pre-activations could
+ *            reach 960 (tansig has no clamp) with the DMMA engine altogether;
  *   DMMA:    FP64 tensor-core contraction (mma.sync.m8n8k4.f64). */
 #define SDPCS_NN_TCGEN05 0
 #define SDPCS_NN_DMMA 1

@@ -69,7 +69,9 @@ keys = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
-        "lts__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
+        "lts__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+        "lts__t_sectors.sum", "lts__t_sectors.sum.per_second", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed"]
 out = ["ncu --set full --clock-control none --import-source on -k 'regex:k_score_feas|k_prep_i8|k_mlp_i8' -c 3 python bench.py --steps 1 --warmup 1 --no-cpu-baseline",
        "(cfg4; k_score_feas: whole shard of 234,531,275 candidates; k_prep_i8 / k_mlp_i8: first staging chunk (262,144 tiles = 33,554,432 candidates since v7; 65,536 tiles before))"]
 dram = {}
@@ -87,6 +89,13 @@ for r in rr[2:]:
                 continue
             if v > 0.15:
                 out.append("   %-72s %s" % (hh.replace("smsp__average_warps_issue_stalled_", "stall ").replace("_per_issue_active.ratio", ""), r[i]))
+    try:   # achieved gather rates (north_star: "achieved HBM/L2 GB/s for the gather"): 32-byte sectors over the kernel's duration
+        dur_s = float(r[h.index("gpu__time_duration.sum")].replace(",", "")) * UNIT[units[h.index("gpu__time_duration.sum")]] * 1e-3
+        l1 = float(r[h.index("l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum")].replace(",", "")) * 32
+        l2 = float(r[h.index("lts__t_sectors.sum")].replace(",", "")) * 32
+        out.append("   %-72s L1 global loads %.2f GB = %.0f GB/s; L2 traffic %.2f GB = %.0f GB/s" % ("gather / staging rates (derived)", l1 / 1e9, l1 / 1e9 / dur_s, l2 / 1e9, l2 / 1e9 / dur_s))
+    except (ValueError, KeyError):
+        pass
     dram[name] = (float(r[h.index("dram__bytes_read.sum")].replace(",", "")) * UNIT[units[h.index("dram__bytes_read.sum")]]
                   + float(r[h.index("dram__bytes_write.sum")].replace(",", "")) * UNIT[units[h.index("dram__bytes_write.sum")]])
 open(os.path.join(P, "ncu_score_%s_cfg4_summary.txt" % ver), "w").write("\n".join(out) + "\n")
