@@ -95,6 +95,25 @@ def test_out_of_range_inputs_fall_back_to_dmma(capi, blobs):
     assert eng.timings()["nn_fallbacks"] == 1
 
 
+def test_weights_outside_the_tansig_range_are_served_by_dmma(capi, blobs):
+    """sdpcs_set_weights bounds the scaled pre-activations of every layer from the weights; the tcgen05 engines' tansig has no
+    clamp, so a net that could reach |z| >= 960 (here: first-layer weights x 2000) is evaluated by the FP64 DMMA engine --
+    silently, correctly and without counting a fall-back."""
+    rho = 3
+    blob = np.array(blobs[rho], dtype=np.float64).copy()
+    n_in, h = int(blob[0]), int(blob[2])
+    off = 3 + 2 * n_in
+    blob[off:off + h * n_in] *= 2000.0                           # W_1
+    eng = capi.Engine(0)
+    eng.set_weights(rho, blob)
+    x = nn_inputs(rho, 500, seed=21)
+    y = eng.nn_eval(rho, x)
+    assert np.abs(y - orc.nn_eval(blob, x)).max() < 1e-9
+    assert eng.timings()["nn_fallbacks"] == 0
+    eng.set_params(nn_engine=capi.NN_DMMA)
+    assert np.array_equal(y, eng.nn_eval(rho, x))                # bit for bit the DMMA engine's answer
+
+
 @pytest.mark.parametrize("rho", [3, 4, 5])
 def test_cover_scores_both_engines(capi, blobs, rho):
     """whole all-subsets cover: tcgen05 and DMMA engines give the same combined selection and scores within 1e-9."""
