@@ -214,6 +214,13 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint3
 // named barrier among the four epilogue warps of one TMEM lane quarter (they share an SM sub-partition): keeps them
 // in lock-step so that no warp is left to finish a step alone at single-warp issue rate
 __device__ __forceinline__ void quarter_sync(int q) { asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory"); }
+// Named barriers for the hand-offs from the 16 epilogue warps to the MMA issuer (staged inputs): the epilogue warps arrive
+// without waiting, the issuer warp blocks in the hardware barrier unit (like the idle helper warps that wait for the end of the
+// kernel in bar.sync) instead of polling an mbarrier.
+constexpr int I8_NB_EMPTY = 1, I8_NB_ACT = 3;             // named barrier ids: empty[stage 0..1], act_ready[lane 0..1]
+constexpr int I8_NB_COUNT = (I8_EPI_WARPS + 1) * 32;     // 16 arriving warps + the issuer warp
+__device__ __forceinline__ void nb_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(I8_NB_COUNT) : "memory"); }
+__device__ __forceinline__ void nb_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(I8_NB_COUNT) : "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -283,7 +290,11 @@ __device__ __forceinline__ void tansig_scaled_vec(const double (&zs)[W], double 
     for (int i = 0; i < W; ++i) q[i] = q[i] * s[i];
 #pragma unroll
     for (int i = 0; i < W; ++i) {
+#ifdef SDPCS_I8_ABL_TAB
+        const double Tj = T[0];          // ablation (trace builds): no table look-up traffic, wrong values
+#else
         const double Tj = T[idx[i] & 255];
+#endif
         const double t0 = fma(Tj, q[i], Tj);
         t[i] = __hiloint2double(__double2hiint(t0) + (int)((uint32_t)(idx[i] & ~255) << 12), __double2loint(t0));
     }
@@ -393,7 +404,11 @@ __device__ __forceinline__ void tansig4_woven(const double (&zs)[4], double (&ou
     side(i8_stage<4>{});
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
+#ifdef SDPCS_I8_ABL_TAB
+        const double Tj = T[0];          // ablation (trace builds): no table look-up traffic, wrong values
+#else
         const double Tj = T[idx[i] & 255];
+#endif
         const double t0 = fma(Tj, q[i], Tj);
         t[i] = __hiloint2double(__double2hiint(t0) + (int)((uint32_t)(idx[i] & ~255) << 12), __double2loint(t0));
     }
@@ -873,12 +888,15 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                     const uint32_t st = step % STAGES, use = step / STAGES;
                     I8_STAMP(step, 0);
                     if (l == 0) ok = mbar_wait(B_A0 + 8 * ln, (uint32_t)p & 1, abort_flag, a.status);
+                    else if constexpr (D == 0) nb_sync(I8_NB_ACT + ln);
                     else {
                         ok = mbar_wait(B_ACT + 8 * ln, actc[ln] & 1, abort_flag, a.status);
                         actc[ln]++;
                     }
                     I8_STAMP(step, 1);
-                    if (ok) ok = mbar_wait(B_EMPTY + 8 * st, (use & 1) ^ 1, abort_flag, a.status);
+                    if constexpr (D == 0) {
+                        if (use > 0) nb_sync(I8_NB_EMPTY + st);          // the first use of a stage has nothing to wait for
+                    } else if (ok) ok = mbar_wait(B_EMPTY + 8 * st, (use & 1) ^ 1, abort_flag, a.status);
                     ok = __all_sync(0xffffffffu, ok);
                     if (!ok) break;
                     I8_STAMP(step, 2);
@@ -968,7 +986,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                         tmem_wait_ld();
                         tc_fence_before();
                         __syncwarp();
-                        mbar_arrive_lane0(B_EMPTY + 8 * st, lane);
+                        if constexpr (D == 0) nb_arrive(I8_NB_EMPTY + st);
+                        else mbar_arrive_lane0(B_EMPTY + 8 * st, lane);
                         I8_STAMP(step, 2);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) z[8 + j] = i8_recombine<NS>(v, j, csbs[8 + j]);
@@ -1043,7 +1062,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                     if (l < NHID - 1) {
                         fence_async_smem();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(B_ACT + 8 * ln);
+                        if constexpr (D == 0) nb_arrive(I8_NB_ACT + ln);
+                        else if (lane == 0) mbar_arrive(B_ACT + 8 * ln);
                     } else {
                         // linear output layer (neural_net_3D.m:61-65, 81-85): partial dot products per column quarter
                         double* yp = (STAGES == 2) ? reinterpret_cast<double*>(sm + L::OFF_Y) + (2 * ln + ((int)p & 1)) * (4 * I8_M)
@@ -1071,6 +1091,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                     ++step;
                 }
     }
+    // a protocol time-out (status 1) cannot be waited out when the issuer is parked in a named barrier: end the grid instead
+    if (D == 0 && *abort_flag) asm volatile("trap;");
     tc_fence_before();
     __syncthreads();
     if (warp == I8_EPI_WARPS)
