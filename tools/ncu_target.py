@@ -3,8 +3,8 @@
 
     cfg4 instance (n = 125, rho = 5), the first 33,554,432 candidates (= one staging chunk of 262,144 tiles):
       k_score_feas<5>                      eigenvalue scores
-      k_prep_i8<5,7> + k_mlp_i8<4,0,7>     FP64-accurate NN engine (7 digits, one TMEM stage)
-      k_prep_i8<5,4> + k_mlp_i8<4,0,4>     screening NN engine (4 digits, two TMEM stages)
+      k_prep_i8<5,7> + k_mlp_i8<4,0,7,0>   FP64-accurate NN engine (7 digits, one TMEM stage)
+      k_prep_i8<5,4> + k_mlp_i8<4,0,4,0>   screening NN engine (4 digits, two TMEM stages)
       k_sel_hist / scan / collect / rank_sort / finish / gather    one combined selection (strong-prefix path)
 
     python tools/ncu_target.py            # plain run first (must exit 0), then the same line under ncu
