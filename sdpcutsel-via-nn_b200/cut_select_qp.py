@@ -24,6 +24,8 @@ strat 3 (exact optimality: the rho-dimensional SDP the reference hands to Mosek)
 exact) run on the batched SDP solver of sdp_kernels.cuh.  Out of scope and raising NotImplementedError: strat 5
 (random shuffle), ch_ext 1 / 2 (chompack chordal extension).
 """
+import operator
+
 import numpy as np
 
 from . import _capi, cover, neartie, nn_weights
@@ -45,6 +47,18 @@ class RankList(list):
     n_violated = 0
     degenerate = 0
     n_near_ties = 0
+    _rows = None        # (len, dim) int16 index tuples (-1 padded) and scores the entries were built from: lets
+    _scores = None      # _gen_eigcuts_selected skip the walk over the entries while the list is still as returned
+    _ends = ()
+
+    def _seal(self, rows, scores):
+        self._rows, self._scores, self._ends = rows, scores, tuple(self)
+
+    def _sealed_rows(self):
+        """The arrays behind the entries if the list still holds exactly the entries it was returned with, in that order."""
+        if self._rows is None or len(self) != len(self._ends) or not all(map(operator.is_, self, self._ends)):
+            return None
+        return self._rows, self._scores
 
 
 class _RowSink(object):
@@ -222,11 +236,14 @@ class B200CutSelection(object):
         out.degenerate, out.n_near_ties = int(res["degenerate"]), int(res["n_near_ties"])
         X_vals, x_vals = vars_values[:nb_lifted], vars_values[nb_lifted:]
         # the reference's tuples, built column-wise (numpy gathers + tolist) instead of entry by entry
-        sets, xinds, sizes, pts, Xs = self._entry_columns(agg, res["idx"], x_vals, X_vals, with_values=(strat_eff != 1))
+        rows = self._set_rows(agg, res["idx"])
+        sets, xinds, sizes, pts, Xs = self._entry_columns(agg, res["idx"], x_vals, X_vals, with_values=(strat_eff != 1), rows=rows)
         if strat_eff == 1:
             out.extend(zip(sets, res["score"].tolist(), xinds, sizes))                # cut_select_qp.py:649
+            out._seal(rows.astype(np.int16), res["score"])
             return out
         out.extend(zip(res["idx"].tolist(), res["score"].tolist(), pts, Xs))          # cut_select_qp.py:599
+        out._seal(rows.astype(np.int16), res["score"])
         if strat_eff == 4:
             return (int(res["new_strat"]), out)                                    # cut_select_qp.py:629-630
         return out
@@ -264,31 +281,33 @@ class B200CutSelection(object):
         std_dev_exact = np.std(exact[o_ex[:sel_size]])
         return rank_list, int((by_est & by_ex).sum()) / sel_size, std_dev_exact, this_round_cuts
 
-    def _entry_columns(self, agg, idx, x_vals, X_vals, with_values):
-        """Per selected candidate: set_inds list, Xarr_inds list (cut_select_qp.py:530-531), size, and -- for the optimality
-        formats -- curr_pt / X_slice tuples (:573-574).  Grouped by subset size so that everything is array work."""
-        rows = self._set_rows(agg, idx)
+    def _entry_columns(self, agg, idx, x_vals, X_vals, with_values, rows=None):
+        """Per selected candidate: set_inds list, Xarr_inds list and size (cut_select_qp.py:530-531; the feasibility format,
+        with_values False) or the curr_pt / X_slice tuples (:573-574; the optimality formats, with_values True).  Grouped by
+        subset size so that everything is array work; the columns the format does not use come back as lists of None."""
+        if rows is None:
+            rows = self._set_rows(agg, idx)
         m, n = rows.shape[0], self._nb_vars
         sets, xinds, pts, Xs = [None] * m, [None] * m, [None] * m, [None] * m
         sizes = (rows >= 0).sum(axis=1)
-        for d in np.unique(sizes):
-            where = np.nonzero(sizes == d)[0]
-            sub = rows[where, :d]
+        for d in (np.unique(sizes) if m else ()):
+            whole = bool((sizes == d).all())
+            where = None if whole else np.nonzero(sizes == d)[0]
+            sub = rows[:, :d] if whole else rows[where, :d]
             pt = neartie._pairs(int(d))
             a, b = sub[:, pt[:, 0]], sub[:, pt[:, 1]]
             xi = n * a - a * (a + 1) // 2 + b
-            cols = [sub.tolist(), xi.tolist()]
-            if with_values:
-                cols += [list(map(tuple, x_vals[sub].tolist())), list(map(tuple, X_vals[xi].tolist()))]
-            if where.size == m:
-                sets, xinds = cols[0], cols[1]
-                if with_values:
-                    pts, Xs = cols[2], cols[3]
+            if with_values:      # tuples straight out of zip over the columns
+                cols = [None, None, list(zip(*x_vals[sub].T.tolist())), list(zip(*X_vals[xi].T.tolist()))]
             else:
-                for j, p in enumerate(where.tolist()):
-                    sets[p], xinds[p] = cols[0][j], cols[1][j]
-                    if with_values:
-                        pts[p], Xs[p] = cols[2][j], cols[3][j]
+                cols = [sub.tolist(), xi.tolist(), None, None]
+            if whole:
+                sets, xinds, pts, Xs = [c if c is not None else [None] * m for c in cols]
+            else:
+                for dst, col in zip((sets, xinds, pts, Xs), cols):
+                    if col is not None:
+                        for j, p in enumerate(where.tolist()):
+                            dst[p] = col[j]
         return sets, xinds, sizes.tolist(), pts, Xs
 
     def _select_resolved(self, eng, agg, strat, vars_values, k):
@@ -359,7 +378,17 @@ class B200CutSelection(object):
         if vars_values is None:
             vars_values = self._last_vars_values                                   # opt entries carry their own point
         packed = None
-        if opt_sel:
+        sealed = rank_list._sealed_rows() if type(rank_list) is RankList else None
+        if sealed is not None:
+            # the list is the one _sel_eigcut_by_ordering_on_measure returned: its index tuples are at hand as an array
+            rows, scores = sealed
+            m = sel_size
+            if opt_sel and strong_only:                                           # cut_select_qp.py:725-726
+                weak = np.nonzero(scores[:sel_size] <= 0)[0]
+                m = int(weak[0]) if weak.size else sel_size
+            if m:
+                packed = rows[:m]
+        elif opt_sel:
             idxs = []
             for ix in range(sel_size):
                 entry = rank_list[ix]

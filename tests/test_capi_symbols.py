@@ -38,6 +38,19 @@ def test_host_utilities_without_gpu(lib):
     assert pkg._capi.binom(125, 5) == 234531275 and pkg._capi.binom(125, 4) == 9691375
     with pytest.raises(pkg._capi.SdpcsError):
         pkg._capi.unrank(10, 3, [120])
+    # triangle rows (cut_select_qp.py:846-860): every rank of small n, both ends of n = 250, all four inequality types
+    for n in (3, 4, 9, 31, 250):
+        T = pkg._capi.binom(n, 3)
+        ranks = np.arange(T) if T < 5000 else np.concatenate([np.arange(3000), np.arange(T - 3000, T), np.arange(0, T, 997)])
+        for t in range(4):
+            csr = pkg._capi.triangle_rows_csr(n, ranks, np.full(ranks.size, t, np.int8))
+            i1, i2, i3 = pkg._capi.unrank(n, 3, ranks).astype(np.int64).T
+            ptr, L = csr["rowptr"][:-1], n * (n + 1) // 2
+            assert np.array_equal(np.diff(csr["rowptr"]), np.full(ranks.size, 6 if t == 3 else 4))
+            assert np.array_equal(csr["ind"][ptr], n * i1 - i1 * (i1 + 1) // 2 + i2)
+            assert np.array_equal(csr["ind"][ptr + 1], n * i1 - i1 * (i1 + 1) // 2 + i3)
+            assert np.array_equal(csr["ind"][ptr + 2], n * i2 - i2 * (i2 + 1) // 2 + i3)
+            assert np.array_equal(csr["ind"][ptr + 3], (i1, i2, i3, i1)[t] + L)
 
 
 def test_no_cpu_fallback_without_device(lib):

@@ -70,6 +70,39 @@ def test_cfg1_optimality_and_combined_round(golden, strat):
         assert isinstance(cs._sel_eigcut_by_ordering_on_measure(4, vv, 1, sel_size=0), list)
 
 
+@pytest.mark.parametrize("strat", [1, 2, 4])
+def test_cut_rows_do_not_depend_on_the_rank_list_shortcut(golden, strat):
+    """_gen_eigcuts_selected takes the index tuples from the arrays behind a RankList it produced itself; a list the caller
+    copied, sliced or re-ordered goes through the entries (cut_select_qp.py:713-735) -- both give the same rows."""
+    n, Q_arr, adj = inst_arrays(golden, "spar030-060-1")
+    cs = pkg.CutSolver()
+    cs.set_instance(Q_arr, adj, n, dim=3)
+    cs._load_neural_nets()
+    cs._get_sdp_vertex_cover(3, ch_ext=-1)
+    vv = golden["cfg1_vars"]
+    k = 406
+    out = cs._sel_eigcut_by_ordering_on_measure(strat, vv, 1, sel_size=k)
+    rl = out[1] if strat == 4 else out
+    assert rl._sealed_rows() is not None
+
+    def rows_for(lst, kk, **kw):
+        cs._my_prob.linear_constraints.rows = []
+        nb = cs._gen_eigcuts_selected(strat, kk, lst, vars_values=vv, **kw)
+        return nb, [(sp.ind, sp.val, rhs) for sp, rhs, _ in rows_of(cs)]
+
+    for kk in (k, 17, 0):
+        assert rows_for(rl, kk) == rows_for(list(rl), kk)
+    if strat != 1:
+        assert rows_for(rl, k, strong_only=True) == rows_for(list(rl), k, strong_only=True)
+    # a re-ordered list is no longer the sealed one: the entries decide
+    rl[1], rl[2] = rl[2], rl[1]
+    assert rl._sealed_rows() is None
+    assert rows_for(rl, 5) == rows_for(list(rl), 5)
+    del rl[3:]
+    assert rl._sealed_rows() is None
+    assert rows_for(rl, 5)[0] <= 3
+
+
 def test_cfg2_rounds_and_triangles(golden):
     n, Q_arr, adj = inst_arrays(golden, "spar125-075-1")
     cs = pkg.CutSolver()
