@@ -393,6 +393,8 @@ def main():
                     help="NN_rhoD evaluation: int8-sliced tcgen05 contraction (default) or FP64 DMMA")
     ap.add_argument("--fused-prep", action="store_true",
                     help="tcgen05 engine: build the layer-0 digit images in the MLP kernel's producer warps (no image in HBM)")
+    ap.add_argument("--separate-eig", action="store_true",
+                    help="tcgen05 engine: lam_min by its own kernel (k_score_feas) instead of inside the staging kernel (A/B)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -429,7 +431,7 @@ def main():
         eng = pkg._capi.Engine(local_rank)
         eng.set_stream(stream.cuda_stream)
         g_obj = max(1e-12, 4e-12 * rho * float(np.abs(Q_arr).max()))
-        eng.set_params(nn_engine=pkg._capi.NN_DMMA if args.nn_engine == "dmma" else pkg._capi.NN_TCGEN05, nn_fused_prep=int(args.fused_prep),
+        eng.set_params(nn_engine=pkg._capi.NN_DMMA if args.nn_engine == "dmma" else pkg._capi.NN_TCGEN05, nn_fused_prep=1 if args.fused_prep else 2 if args.separate_eig else 0,
                        guard_lam=1e-12, guard_obj=g_obj)
         eng.set_weights(rho, blobs[rho])
         eng.set_instance(n, Q_arr)
@@ -573,8 +575,10 @@ def main():
             nhid = 4 if rho == 5 else 3
             i8_ops = 28 * (32 + (nhid - 1) * 64) * 64 * 2
             i8_tops = n_local * i8_ops / (nn_ms_step * 1e-3) * 1e-12
+            eig = "k_score_feas<%d> (FP64 tridiagonal + Laguerre)" % rho if (args.separate_eig or args.fused_prep or args.strat != 4) else \
+                  "lam_min (FP64 tridiagonal + Laguerre) inside k_prep_i8<%d,7,FEAS>: nn_kernels_ms includes it" % rho
             kname = "k_mlp_i8<%d> (tcgen05.mma kind::i8, FP64-accurate 7x7-digit slicing of the FP64 MLP, TMEM accumulators) " \
-                    "+ k_prep_i8<%d> + k_score_feas<%d> (FP64 tridiagonal + Laguerre)" % (nhid, rho, rho)
+                    "+ k_prep_i8<%d> + %s" % (nhid, rho, eig)
             extra = dict(nn_kernels_ms=nn_ms_step, int8_tensor=dict(achieved=i8_tops, peak=2 * bf16, unit="TOP/s", frac=i8_tops / (2 * bf16),
                                                                   ops_per_subset=i8_ops, peak_source=bf16_src),
                          note="achieved / peak / frac are FP64-EQUIVALENT: algorithmic FP64 flop of SURVEY 8(d) over the measured FP64 DMMA peak "

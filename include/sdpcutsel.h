@@ -48,8 +48,10 @@ typedef struct sdpcs_params {
     int32_t jacobi_sweeps;   /* scoring: 0 = Householder tridiagonalisation + Laguerre (default), > 0 = cyclic
                               * Jacobi with that many sweeps; cut generation always uses Jacobi (needs vectors) */
     int32_t nn_engine;       /* NN_rhoD evaluation: SDPCS_NN_TCGEN05 (default) or SDPCS_NN_DMMA */
-    int32_t nn_fused_prep;   /* tcgen05 engine: 0 = layer-0 digit images staged through HBM by a separate kernel (default),
-                              * 1 = built in shared memory by producer warps of the MLP kernel (no image in HBM) */
+    int32_t nn_fused_prep;   /* tcgen05 engine: 0 = layer-0 digit images staged through HBM by a separate kernel (default), which
+                              * also computes lam_min when a call asks for both scores (one unranking + gather per candidate);
+                              * 1 = images built in shared memory by producer warps of the MLP kernel (no image in HBM);
+                              * 2 = like 0 but lam_min always by its own kernel (the arrangement 0 replaced, kept for A/B) */
     /* Near-tie guard (SURVEY 7 hard part 1).  The reference's order among candidates whose scores agree to rounding
      * noise is decided by LAPACK dsyevd / libm exp round-off (cut_select_qp.py:647-654, 599-601); device scores differ
      * from those by <= ~1e-14 (lam) / ~1e-10 (obj).  With a guard > 0 a selection also returns every candidate ranked

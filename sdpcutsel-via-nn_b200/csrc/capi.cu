@@ -43,6 +43,7 @@ struct sdpcs_ctx {
     int* d_status = nullptr;       // device status word of the tcgen05 pipeline
     int* h_status = nullptr;       // pinned
     bool i8_used = false;
+    bool fuse_feas = false;          // this scoring call: lam_min comes out of k_prep_i8<.., FEAS> (set by score_device)
     // cover
     int rho = 0, mode = 0;         // mode 0 none, 1 all-subsets, 2 list
     i64 N = 0, base = 0;           // base = agg_idx of local candidate 0 (rank_begin / agg_offset)
@@ -809,7 +810,7 @@ static int launch_mlp_i8(sdpcs_ctx* ctx, const MlpI8Args& m)
 
 // optimality measure of the N candidates described by `a` through the tcgen05 int8-sliced MLP, layer-0 digit images
 // staged through HBM in chunks by k_prep_i8 (default: faster today) --
-template <int D, int NS>
+template <int D, int NS, bool FEAS>
 static int launch_nn_i8_staged(sdpcs_ctx* ctx, const ScoreArgs& a, i64 N)
 {
     const uint8_t* wimg = (NS == I8_NS) ? ctx->d_wi8[D] : ctx->d_wi8s[D];
@@ -818,7 +819,7 @@ static int launch_nn_i8_staged(sdpcs_ctx* ctx, const ScoreArgs& a, i64 N)
     int rc = ensure_tiles(ctx, std::min<i64>(total_tiles, I8_CHUNK_TILES), I8Dig<NS>::TILE_BYTES);
     if (rc) return rc;
     int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_prep_i8<D, NS>, 256, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_prep_i8<D, NS, FEAS>, 256, 0));
     for (i64 c0 = 0; c0 < N; c0 += I8_CHUNK_TILES * I8_M) {
         const i64 rows = std::min<i64>(N - c0, I8_CHUNK_TILES * I8_M);
         const i64 nt = (rows + I8_M - 1) / I8_M;
@@ -826,7 +827,7 @@ static int launch_nn_i8_staged(sdpcs_ctx* ctx, const ScoreArgs& a, i64 N)
         pa.s = a; pa.c0 = c0; pa.n_rows = rows; pa.tiles = ctx->d_tiles; pa.status = ctx->d_status;
         const i64 groups = nt * (I8_M / 32);
         const i64 pgrid = std::min<i64>((groups + 7) / 8, (i64)ctx->sms * std::max(occ, 1));
-        k_prep_i8<D, NS><<<(unsigned)std::max<i64>(pgrid, 1), 256, 0, ctx->stream>>>(pa);
+        k_prep_i8<D, NS, FEAS><<<(unsigned)std::max<i64>(pgrid, 1), 256, 0, ctx->stream>>>(pa);
         CU(cudaGetLastError());
         MlpI8Args m;
         m.wimg = wimg; m.tiles = ctx->d_tiles; m.n_tiles = nt; m.n_rows = rows; m.out_base = c0;
@@ -844,8 +845,11 @@ template <int D>
 static int launch_nn_i8(sdpcs_ctx* ctx, const ScoreArgs& a, i64 N)
 {
     if (!ctx->d_wi8[D]) return ctx->fail(SDPCS_ERR_STATE, "NN_" + std::to_string(D) + "D weights not set");
-    if (ctx->params.nn_engine == SDPCS_NN_SCREEN) return launch_nn_i8_staged<D, I8_NS_SCREEN>(ctx, a, N);
-    if (!ctx->params.nn_fused_prep) return launch_nn_i8_staged<D, I8_NS>(ctx, a, N);
+    const bool feas = ctx->fuse_feas;       // the staging kernel also produces lam_min (score_device)
+    if (ctx->params.nn_engine == SDPCS_NN_SCREEN)
+        return feas ? launch_nn_i8_staged<D, I8_NS_SCREEN, true>(ctx, a, N) : launch_nn_i8_staged<D, I8_NS_SCREEN, false>(ctx, a, N);
+    if (ctx->params.nn_fused_prep != 1)
+        return feas ? launch_nn_i8_staged<D, I8_NS, true>(ctx, a, N) : launch_nn_i8_staged<D, I8_NS, false>(ctx, a, N);
     MlpI8Args m;
     m.wimg = ctx->d_wi8[D]; m.s = a; m.tiles = nullptr; m.n_tiles = (N + I8_M - 1) / I8_M; m.n_rows = N; m.out_base = 0;
     m.pos = a.pos; m.obj = a.obj; m.dbg_z = nullptr; m.dbg_layer = -1; m.status = ctx->d_status;
@@ -866,7 +870,8 @@ static int launch_score(sdpcs_ctx* ctx, int want, const uint8_t* idx, const i64*
     a.wfrag = ctx->d_wfrag[D]; a.lam = ctx->d_lam; a.obj = ctx->d_obj;
     a.sweeps = ctx->params.jacobi_sweeps > 0 ? ctx->params.jacobi_sweeps : 0;   // 0: tridiagonalisation + Laguerre
     const i64 groups = (N + 31) / 32;
-    if (want & 1) {   // K1+K2+K3: lam_min of every candidate
+    const bool i8_path = ctx->params.nn_engine != SDPCS_NN_DMMA && ctx->i8_ok[D] && a.wfrag;
+    if ((want & 1) && !(ctx->fuse_feas && i8_path)) {   // K1+K2+K3: lam_min of every candidate (else: by the staging kernel of K4a)
         int occ = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_score_feas<D>, 256, 0));
         i64 grid = std::min<i64>((groups + 7) / 8, (i64)ctx->sms * std::max(occ, 1));
@@ -884,7 +889,7 @@ static int launch_score(sdpcs_ctx* ctx, int want, const uint8_t* idx, const i64*
         return SDPCS_OK;
     }
     if ((want & 2) && !a.wfrag) return ctx->fail(SDPCS_ERR_STATE, "NN_" + std::to_string(D) + "D weights not set");
-    if ((want & 2) && ctx->params.nn_engine != SDPCS_NN_DMMA && ctx->i8_ok[D]) {
+    if ((want & 2) && i8_path) {
         // K1+K2 (k_prep_i8) + K4 on tcgen05 (k_mlp_i8), chunked through the layer-0 digit-image buffer
         int rc = launch_nn_i8<D>(ctx, a, N);
         if (rc) return rc;
@@ -922,6 +927,10 @@ static int score_device(sdpcs_ctx* ctx, int want)
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     int rc = SDPCS_OK;
     ctx->ev_nn = false;
+    // both scores wanted and the layer-0 images staged by k_prep_i8: that kernel computes lam_min as well (one unranking
+    // and one gather per candidate, eigenvalue arithmetic under the image stores); nn_fused_prep = 2 keeps the launches apart
+    ctx->fuse_feas = (want & 3) == 3 && ctx->params.jacobi_sweeps <= 0 && ctx->params.nn_fused_prep == 0 &&
+                     ctx->params.nn_engine != SDPCS_NN_DMMA;
     for (int bit = 1; bit <= 4 && rc == SDPCS_OK; bit <<= 1) {   // all eigenvalue launches, then all NN (or exact SDP) launches
         if (!(want & bit)) continue;
         if (bit >= 2) CU(cudaEventRecord(ctx->ev[6], ctx->stream));

@@ -568,8 +568,14 @@ struct PrepI8Args {
     int* status;
 };
 
-template <int D, int NS>
-__global__ void __launch_bounds__(256) k_prep_i8(PrepI8Args pa)
+// FEAS: the launch also produces lam_min of every candidate (K3, same arithmetic as k_score_feas) from the point it has
+// gathered anyway -- when a call wants both scores the eigenvalue work (FP64 pipe) runs under the image stores (HBM) of
+// the other warps instead of in a launch of its own with its own unranking and gathers.
+#ifndef SDPCS_PREPF_MINB
+#define SDPCS_PREPF_MINB 1
+#endif
+template <int D, int NS, bool FEAS = false>
+__global__ void __launch_bounds__(256, FEAS ? SDPCS_PREPF_MINB : 1) k_prep_i8(PrepI8Args pa)
 {
     using C = NetCfg<D>;
     constexpr int T = D * (D + 1) / 2;
@@ -629,6 +635,10 @@ __global__ void __launch_bounds__(256) k_prep_i8(PrepI8Args pa)
         for (int q = 0; q < T; ++q) p[D + q] = __dadd_rn(__dmul_rn(__dsub_rn(Qs[q], sxo[D + q]), sgn[D + q]), -1.0);
         uint8_t* tile = pa.tiles + (r / I8_M) * (i64)I8Dig<NS>::TILE_BYTES;
         i8_store_row<C::NIN, NS>(tile, (int)(r % I8_M), p, __dmul_rn(-s, max_elem), max_elem, valid, pa.status);
+        if constexpr (FEAS) {
+            const double lam = lam_min_subset<D>(xs, Xs, 0);
+            if (valid) a.lam[a.pos ? __ldg(a.pos + pa.c0 + r) : pa.c0 + r] = lam;
+        }
         if (all_mode && g + 1 < g1) {
             if (!(valid && lex_advance<D>(a.n, c, 32))) {
 #pragma unroll
