@@ -202,6 +202,56 @@ def test_fused_producer_is_bit_identical_to_the_staged_images(capi, blobs, golde
 
 
 @pytest.mark.parametrize("rho", [2, 3, 4, 5])
+@pytest.mark.parametrize("engine", ["exact", "screen"])
+def test_eigenvalue_score_from_the_staging_kernel_is_bit_identical(capi, blobs, golden, rho, engine):
+    """A call that wants both scores (want = 3, the combined rule) gets lam_min from k_prep_i8<.., FEAS> -- the arithmetic of
+    k_score_feas on the point the staging kernel has gathered anyway.  nn_fused_prep = 2 keeps the two launches apart: lam
+    and obj must agree bit for bit, on ragged all-subsets shards and on a mixed-size list cover, and with the scores of
+    separate want = 1 / want = 2 calls."""
+    n = 29
+    Q_arr, adj = orc.boxqp_arrays(orc.synth_instance(n, 0.7, seed=50 + rho))
+    vv = orc.synth_point(n, seed=9)
+    N = capi.binom(n, rho)
+    out = []
+    for mode in (0, 2):
+        eng = capi.Engine(0)
+        eng.set_params(nn_fused_prep=mode, nn_engine=capi.NN_SCREEN if engine == "screen" else capi.NN_TCGEN05)
+        for d in range(2, rho + 1):
+            eng.set_weights(d, blobs[d])
+        eng.set_instance(n, Q_arr)
+        res = []
+        for r0, r1 in ((0, N), (N // 3 + 5, 2 * N // 3 + 77), (7, 8)):
+            eng.set_cover_all(rho, r0, r1)
+            eng.score(vv, 3)
+            launches = eng.timings()["score_launches"]
+            res.append(eng.scores())
+            if mode == 0:
+                eng.score(vv, 1)
+                lam1 = eng.scores(obj=False)[0]
+                eng.score(vv, 2)
+                obj2 = eng.scores(lam=False)[1]
+                assert np.array_equal(lam1, res[-1][0]) and np.array_equal(obj2, res[-1][1])
+        assert launches == (2 if mode == 0 else 3)
+        if rho >= 3:
+            n2, Q2, adj2 = __import__("conftest").inst_arrays(golden, "spar040-030-1")
+            idx, sizes = orc.cover_pattern_E(adj2, rho)
+            eng2 = capi.Engine(0)
+            eng2.set_params(nn_fused_prep=mode, nn_engine=capi.NN_SCREEN if engine == "screen" else capi.NN_TCGEN05)
+            for d in range(2, rho + 1):
+                eng2.set_weights(d, blobs[d])
+            eng2.set_instance(n2, Q2)
+            eng2.set_cover_list(rho, idx)
+            eng2.score(golden["mix_vars"], 3)
+            res.append(eng2.scores())
+            assert eng2.timings()["nn_fallbacks"] == 0
+        assert eng.timings()["nn_fallbacks"] == 0
+        out.append(res)
+    for (la, oa), (lb, ob) in zip(*out):
+        assert np.array_equal(la, lb) and np.array_equal(oa, ob)
+        assert np.isfinite(la).all() and np.isfinite(oa).all()
+
+
+@pytest.mark.parametrize("rho", [2, 3, 4, 5])
 def test_screening_engine_matches_its_integer_model(capi, blobs, rho):
     """SDPCS_NN_SCREEN: the same pipeline with 4-digit operands and two TMEM accumulator stages.  Layer by layer against the
     integer model with ns = 4 (exact integer sums: layer 0 agrees to the last bits), outputs within 1e-5 of NNs.so's
