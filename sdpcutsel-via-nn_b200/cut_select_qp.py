@@ -3,7 +3,7 @@
 Same method names, argument meaning, return formats and error behaviour as the reference for
     _load_neural_nets              (cut_select_qp.py:284-303)
     _get_sdp_vertex_cover          (cut_select_qp.py:377-541)
-    _sel_eigcut_by_ordering_on_measure (cut_select_qp.py:543-703, strat 1, 2, 3, 4, -1)
+    _sel_eigcut_by_ordering_on_measure (cut_select_qp.py:543-703, strat 1, 2, 3, 4, 5, -1)
     _gen_eigcuts_selected          (cut_select_qp.py:705-755)
     _get_eigendecomp               (cut_select_qp.py:788-797)
     __preprocess_triangle_ineq / __separate_and_add_triangle (cut_select_qp.py:799-863)
@@ -21,8 +21,9 @@ runs of entries closer than the guard are re-scored with the reference's own ari
 NN function, ``neartie.py``) and re-sorted, so that the prefix equals the reference's also on LP vertices where
 thousands of candidates tie; ``RankList.degenerate`` / ``n_near_ties`` report what happened.
 strat 3 (exact optimality: the rho-dimensional SDP the reference hands to Mosek) and strat -1 (figure 8: estimate vs
-exact) run on the batched SDP solver of sdp_kernels.cuh.  Out of scope and raising NotImplementedError: strat 5
-(random shuffle), ch_ext 1 / 2 (chompack chordal extension).
+exact) run on the batched SDP solver of sdp_kernels.cuh.  strat 5 (random) shuffles the cover with numpy's legacy generator
+exactly like the reference (same permutation for the same seed) and cuts its first sel_size entries on the device.
+Out of scope and raising NotImplementedError: ch_ext 1 / 2 (chompack chordal extension).
 """
 import operator
 
@@ -211,9 +212,9 @@ class B200CutSelection(object):
 
     def _sel_eigcut_by_ordering_on_measure(self, strat, vars_values, cut_round, sel_size=0):
         if strat == 5:
-            raise NotImplementedError("strat 5 (random shuffle of agg_list) is outside the GPU hot path")
+            return self._random_order()
         if strat not in (1, 2, 3, 4, -1):
-            raise ValueError("strat must be 1 (feasibility), 2 (optimality), 3 (exact SDP), 4 (combined) or -1 (figure 8)")
+            raise ValueError("strat must be 1 (feasibility), 2 (optimality), 3 (exact SDP), 4 (combined), 5 (random) or -1 (figure 8)")
         if strat == -1:
             return self._figure_8(vars_values, cut_round, sel_size)
         agg = self._agg_view()
@@ -247,6 +248,28 @@ class B200CutSelection(object):
         if strat_eff == 4:
             return (int(res["new_strat"]), out)                                    # cut_select_qp.py:629-630
         return out
+
+    _SHUFFLE_MAX_SUBS = 5 * 10 ** 7
+
+    def _random_order(self):
+        """strat 5 (cut_select_qp.py:634-637): ``np.random.shuffle(agg_list)`` in place, the shuffled cover is the ranking.
+        numpy's legacy shuffle draws the same sequence for a list and for an index array of the same length, so the
+        permutation is the reference's for the same ``np.random.seed``; like there the cover STAYS shuffled (agg_idx of later
+        rounds are positions in the shuffled list).  The lazy cover becomes a list cover in the new order; its device
+        context is dropped and rebuilt on the next scoring call."""
+        agg = self._agg_list
+        if not isinstance(agg, cover.AggList):
+            np.random.shuffle(agg)                                    # a plain list of reference tuples: the reference's statement
+            self.__dict__.get("_adopted", {}).pop(id(agg), None)
+            return agg
+        N = len(agg)
+        if N > self._SHUFFLE_MAX_SUBS:
+            raise ValueError("random selection materialises the shuffled cover; %d sub-problems are too many" % N)
+        perm = np.arange(N, dtype=np.int64)
+        np.random.shuffle(perm)
+        agg.idx = self._set_rows(agg, perm + agg.offset).astype(np.int16)
+        agg.n_all, agg._engine = None, None
+        return agg
 
     _FIG8_MAX_SUBS = 2 * 10 ** 6
 
@@ -371,15 +394,17 @@ class B200CutSelection(object):
 
     def _gen_eigcuts_selected(self, strat, sel_size, rank_list, strong_only=False, vars_values=None):
         opt_sel, feas_sel, rand_sel = (strat in [2, 3, 4, -1]), (strat == 1), (strat == 5)
-        if rand_sel:
-            raise NotImplementedError("random selection (strat 5) is outside the GPU hot path")
         my_prob = self._my_prob
         sel_size = min(sel_size, len(rank_list))                                   # cut_select_qp.py:713
         if vars_values is None:
             vars_values = self._last_vars_values                                   # opt entries carry their own point
         packed = None
         sealed = rank_list._sealed_rows() if type(rank_list) is RankList else None
-        if sealed is not None:
+        if isinstance(rank_list, cover.AggList):
+            # random selection hands the (shuffled) cover itself over (cut_select_qp.py:636-637, 728-731): its first rows
+            if sel_size:
+                packed = self._set_rows(rank_list, np.arange(sel_size, dtype=np.int64) + rank_list.offset).astype(np.int16)
+        elif sealed is not None:
             # the list is the one _sel_eigcut_by_ordering_on_measure returned: its index tuples are at hand as an array
             rows, scores = sealed
             m = sel_size

@@ -132,6 +132,27 @@ def test_boxqp_loop_follows_the_reference_vertex_for_vertex(filename, strat):
 
 
 @needs_ref
+@pytest.mark.parametrize("filename", ["spar020-100-1", "spar030-060-1"])
+def test_boxqp_loop_random_selection(filename):
+    """strat 5 (Table 3's random baseline): np.random.shuffle of the cover, cuts from its first sel_size entries.  Same
+    seed -> same permutation (in place, round after round) -> with rows from numpy eigh the whole run equals the reference's."""
+    ref, refq, d = REF
+    import sdpcutsel_via_nn_b200 as pkg
+    GpuSolver0, _ = pkg.make_solvers(ref, refq)
+
+    class GpuSolver(GpuSolver0):
+        _CUT_ROWS_FROM_LAPACK = True
+
+    with refloader.in_reference_dir(d):
+        np.random.seed(7)
+        out_ref = ref.CutSolver().cut_select_algo(filename, 3, 0.1, strat=5, nb_rounds_cuts=3)
+        np.random.seed(7)
+        out_gpu = GpuSolver().cut_select_algo(filename, 3, 0.1, strat=5, nb_rounds_cuts=3)
+    assert out_gpu[4] == out_ref[4] and out_gpu[6] == out_ref[6] and sum(out_ref[4]) > 0
+    assert np.abs(np.array(out_gpu[0]) - np.array(out_ref[0])).max() < 1e-9 * abs(out_ref[0][0])
+
+
+@needs_ref
 @pytest.mark.parametrize("lapack_rows", [False, True])
 def test_boxqp_loop_dense_cuts_and_triangles(lapack_rows):
     """strat 0 (__gen_dense_eigcuts) + triangle separation through the name-mangled private methods, and feasibility

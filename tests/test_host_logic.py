@@ -63,9 +63,41 @@ def test_solver_surface_names():
     assert hasattr(pkg.CutSolverQCQP(), "_CutSolverQCQP__get_vertex_cover")
     assert (cs._THRES_NEG_EIGVAL, cs._BIG_M, cs._SDP_CUTS_PER_ROUND_MAX, cs._TRI_CUTS_PER_ROUND_MAX) == (-1e-15, 1000, 5000, 10000)
     with pytest.raises(NotImplementedError):
-        cs._sel_eigcut_by_ordering_on_measure(5, None, 1)
-    with pytest.raises(NotImplementedError):
         cs._get_sdp_vertex_cover(3, ch_ext=1)
+    with pytest.raises(ValueError):
+        cs._sel_eigcut_by_ordering_on_measure(6, None, 1)
+
+
+def test_random_selection_shuffles_like_the_reference():
+    """strat 5 (cut_select_qp.py:634-637): np.random.shuffle(agg_list) in place.  The lazy cover is permuted with the same
+    draws (numpy's legacy shuffle of an index array of the same length), stays shuffled, and a plain list of reference
+    tuples is shuffled by the very same statement.  Host logic only: no device call before a score is asked for."""
+    import itertools
+    n, dim = 9, 3
+    Q_arr = np.arange(n * (n + 1) // 2, dtype=np.float64) - 7.0
+    ref_list = [tuple(c) for c in itertools.combinations(range(n), dim)]
+    np.random.seed(7)
+    np.random.shuffle(ref_list)
+    ref_twice = list(ref_list)
+    np.random.shuffle(ref_twice)
+
+    cs = pkg.CutSolver()
+    cs.set_instance(Q_arr, np.ones((n, n), dtype=np.uint8), n, dim=dim)
+    cs._agg_list = pkg.cover.AggList(n, dim, Q_arr, n_all=84)
+    np.random.seed(7)
+    out = cs._sel_eigcut_by_ordering_on_measure(5, None, 1)
+    assert out is cs._agg_list and len(out) == 84 and not out.is_all
+    assert [tuple(e[0]) for e in out] == ref_list
+    s, xi, qs, me = out[5]
+    assert xi == pkg.cover.xarr_inds(n, s) and me == dim * np.abs(Q_arr[xi]).max()          # cut_select_qp.py:530-538
+    out2 = cs._sel_eigcut_by_ordering_on_measure(5, None, 2)                                   # the list stays shuffled
+    assert [tuple(e[0]) for e in out2] == ref_twice
+    # a plain list in the reference's own format (the QCQP caller re-points _agg_list to such lists)
+    plain = [(list(c), [], (), 1.0) for c in itertools.combinations(range(n), dim)]
+    cs._agg_list = plain
+    np.random.seed(7)
+    assert cs._sel_eigcut_by_ordering_on_measure(5, None, 1) is plain
+    assert [tuple(e[0]) for e in plain] == ref_list
 
 
 def test_triangle_rows_csr_match_the_reference_rows():
