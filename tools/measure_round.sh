@@ -16,3 +16,5 @@ timeout 900 ncu --set full --clock-control none --import-source on -k "regex:k_s
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-other-configs --no-screened > $O/${TAG}_ncu2.log 2>&1
 timeout 300 python tools/cover_bench.py > $O/${TAG}_cover_bench.log 2>&1; cat $O/${TAG}_cover_bench.log
 timeout 120 python tools/i8_trace.py -q > $O/${TAG}_i8_trace.log 2>&1; timeout 120 python tools/i8_trace.py -q --screen > $O/${TAG}_i8_trace_screen.log 2>&1; head -3 $O/${TAG}_i8_trace.log $O/${TAG}_i8_trace_screen.log
+timeout 300 python bench.py --separate-eig --no-cpu-baseline --no-other-configs --no-screened --steps 4 --warmup 3 > $O/${TAG}_bench_n1_separate_eig.json 2>> $O/${TAG}_bench_n1.err
+timeout 300 python tools/latency_profile.py > $O/${TAG}_latency_profile.log 2>&1; grep "^strat" $O/${TAG}_latency_profile.log

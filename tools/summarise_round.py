@@ -46,11 +46,17 @@ for k, a in agg.items():
     lines.append("%-28s %6d %12.3f %6.1f%% %12.3f %12.3f" % (k[:28], a[0], a[1], 100 * a[1] / tot, a[2] / 1e9, a[3] / 1e9))
 mk = [k for k in agg if k.startswith("k_mlp_i8")][0]
 pk = [k for k in agg if k.startswith("k_prep_i8")][0]
-fk = [k for k in agg if k.startswith("k_score_feas")][0]
+fks = [k for k in agg if k.startswith("k_score_feas")]
 dmma_passes = sum(a[0] for k, a in agg.items() if k.startswith("k_score_nn"))
-passes = max(agg[fk][0] - dmma_passes, 1)             # scoring passes of the tcgen05 engine among the captured launches
-chunks = agg[mk][0] / float(passes)
-per_step = {k: (agg[k][1] / (agg[k][0] / (chunks if k != fk else 1.0)), (agg[k][2] + agg[k][3]) / (agg[k][0] / (chunks if k != fk else 1.0))) for k in (mk, pk, fk)}
+chunks = float(-(-(-(-234531275 // 128)) // 262144))  # staging chunks of one cfg4 pass (I8_CHUNK_TILES = 262,144 tiles): 7
+passes = agg[mk][0] / chunks                          # scoring passes of the tcgen05 engine among the captured launches
+# since the lam_min computation moved into the staging kernel (k_prep_i8<.., FEAS>) the tcgen05 passes launch no
+# k_score_feas; what is left of it in the list belongs to the DMMA cross-check pass
+feas_own = (agg[fks[0]][0] - dmma_passes) if fks else 0
+per_step = {k: (agg[k][1] / passes, (agg[k][2] + agg[k][3]) / passes) for k in (mk, pk)}
+if feas_own > 0:
+    fk = fks[0]
+    per_step[fk] = (agg[fk][1] / agg[fk][0], (agg[fk][2] + agg[fk][3]) / agg[fk][0])
 lines += ["", "per scoring pass over 234,531,275 candidates (%g chunks): " % chunks
           + "; ".join("%s %.1f ms, %.2f GB DRAM" % (k, v[0], v[1] / 1e9) for k, v in per_step.items())]
 open(os.path.join(P, "ncu_launches_cfg4_%s_summary.txt" % ver), "w").write("\n".join(lines) + "\n")
@@ -73,7 +79,7 @@ keys = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "lts__t_sectors.sum", "lts__t_sectors.sum.per_second", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__throughput.avg.pct_of_peak_sustained_elapsed"]
 out = ["ncu --set full --clock-control none --import-source on -k 'regex:k_score_feas|k_prep_i8|k_mlp_i8' -c 3 python bench.py --steps 1 --warmup 1 --no-cpu-baseline",
-       "(cfg4; k_score_feas: whole shard of 234,531,275 candidates; k_prep_i8 / k_mlp_i8: first staging chunk (262,144 tiles = 33,554,432 candidates since v7; 65,536 tiles before))"]
+       "(cfg4; k_prep_i8 (staging + lam_min since pass n) / k_mlp_i8: first staging chunk (262,144 tiles = 33,554,432 candidates); k_score_feas, if listed: whole shard)"]
 dram = {}
 for r in rr[2:]:
     name = r[h.index("Kernel Name")]
@@ -112,7 +118,7 @@ step_bytes = sum(v[1] for v in per_step.values())
 json.dump({"source": "profiles/%s/ncu_launches_cfg4_%s_summary.txt" % (rnd, ver),
            "kernels": {k: {"ms_per_pass": v[0], "dram_bytes_per_pass": v[1]} for k, v in per_step.items()},
            "score_kernel_dram_bytes_per_launch": step_bytes,
-           "note": "one scoring pass over 234,531,275 candidates = 1 x k_score_feas + %g x (k_prep_i8 + k_mlp_i8): dram__bytes_read.sum + " % chunks +
+           "note": "one scoring pass over 234,531,275 candidates = %g x (k_prep_i8 [incl. lam_min] + k_mlp_i8): dram__bytes_read.sum + " % chunks +
                    "dram__bytes_write.sum summed over those launches; algorithmic bytes = 16 B x candidates = 3.75e9 (lam + obj); the rest is the "
                    "layer-0 digit image staged through HBM (156 B per candidate, written by k_prep_i8 and read back by TMA)"},
           open(os.path.join(ROOT, "profiles", "ncu_summary.json"), "w"), indent=1)
