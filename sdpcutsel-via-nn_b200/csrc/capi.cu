@@ -1007,6 +1007,7 @@ static int ensure_out(sdpcs_ctx* ctx, i64 k)
         *p = nullptr;
         CU(cudaMalloc(p, (size_t)k * 8));
     }
+    CU(cudaMemsetAsync(ctx->d_s_perm, 0, (size_t)k * 8, ctx->stream));     // partial ranks / tickets of k_rank_sort: zero between launches
     ctx->out_cap = k;
     return SDPCS_OK;
 }
@@ -1038,8 +1039,13 @@ static void launch_collect_sort(sdpcs_ctx* ctx, const KeySrc& ks, i64 cap, i64 c
 {
     const unsigned cgrid = (unsigned)std::max<i64>(1, std::min<i64>((ks.N + 511) / 512, (i64)ctx->sms * 8));
     k_sel_collect<MODE><<<cgrid, 256, 0, ctx->stream>>>(ks, cap, ctx->d_c_k1, ctx->d_c_k2, ctx->d_c_idx);
-    k_rank_sort<<<(unsigned)((cap_exit + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_state, 0, cap, ctx->d_c_k1, ctx->d_c_k2,
-                                                                                ctx->d_c_idx, ctx->d_s_k1, ctx->d_s_k2, ctx->d_s_idx);
+    // O(m^2) rank counting spread over ~4 blocks per SM: S segments of the list per column of 256 entries; the partial
+    // ranks meet in d_s_perm (zero between launches: the kernel cleans up after itself)
+    const unsigned nbx = (unsigned)((cap_exit + 255) / 256);
+    const unsigned S = (unsigned)std::min<i64>(32, std::max<i64>(1, (4 * (i64)ctx->sms + nbx - 1) / nbx));
+    unsigned* rank = reinterpret_cast<unsigned*>(ctx->d_s_perm);
+    k_rank_sort<<<dim3(nbx, S), 256, 0, ctx->stream>>>(ctx->d_state, 0, cap, ctx->d_c_k1, ctx->d_c_k2, ctx->d_c_idx, ctx->d_s_k1,
+                                                        ctx->d_s_k2, ctx->d_s_idx, rank, rank + ctx->out_cap);
     k_sel_finish<<<1, 32, 0, ctx->stream>>>(ctx->d_state, ctx->d_s_k1, cap, delta);
     ctx->tm.select_launches += 3;
 }
@@ -1414,7 +1420,7 @@ extern "C" int sdpcs_merge_topk(sdpcs_ctx* ctx, int64_t m, const double* score, 
     if (obj2) CU(cudaMemcpyAsync(d_obj2, obj2, m * 8, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(d_idx, idx, m * 8, cudaMemcpyHostToDevice, ctx->stream));
     k_merge_keys<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(m, d_score, obj2 ? d_obj2 : nullptr, d_k1, d_k2);
-    k_rank_sort<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(nullptr, m, m, d_k1, d_k2, d_idx, d_s1, d_s2, d_si);
+    k_rank_sort<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(nullptr, m, m, d_k1, d_k2, d_idx, d_s1, d_s2, d_si, nullptr, nullptr);
     CU(cudaGetLastError());
     std::vector<i64> sorted_idx(m), in_idx(idx, idx + m);
     CU(cudaMemcpyAsync(sorted_idx.data(), d_si, m * 8, cudaMemcpyDeviceToHost, ctx->stream));

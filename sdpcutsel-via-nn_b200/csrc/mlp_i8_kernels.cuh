@@ -571,11 +571,10 @@ struct PrepI8Args {
 // FEAS: the launch also produces lam_min of every candidate (K3, same arithmetic as k_score_feas) from the point it has
 // gathered anyway -- when a call wants both scores the eigenvalue work (FP64 pipe) runs under the image stores (HBM) of
 // the other warps instead of in a launch of its own with its own unranking and gathers.
-#ifndef SDPCS_PREPF_MINB
-#define SDPCS_PREPF_MINB 1
-#endif
+// Two CTAs per SM (<= 128 registers) is the measured optimum for both variants: left to itself ptxas takes 154 registers for
+// FEAS (one CTA per SM, +10 ms per cfg4 step), and three or four CTAs per SM (80 / 64 registers) spill.
 template <int D, int NS, bool FEAS = false>
-__global__ void __launch_bounds__(256, FEAS ? SDPCS_PREPF_MINB : 1) k_prep_i8(PrepI8Args pa)
+__global__ void __launch_bounds__(256, 2) k_prep_i8(PrepI8Args pa)
 {
     using C = NetCfg<D>;
     constexpr int T = D * (D + 1) / 2;
