@@ -404,7 +404,9 @@ __device__ __forceinline__ void tansig4_woven(const double (&zs)[4], double (&ou
     side(i8_stage<4>{});
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-#ifdef SDPCS_I8_ABL_TAB
+#if defined(SDPCS_I8_ABL_TAB) && SDPCS_I8_ABL_TAB == 2
+        const double Tj = 1.0 + 0.001 * (double)(idx[i] & 255);   // ablation (trace builds): no load at all, wrong values
+#elif defined(SDPCS_I8_ABL_TAB)
         const double Tj = T[0];          // ablation (trace builds): no table look-up traffic, wrong values
 #else
         const double Tj = T[idx[i] & 255];
@@ -1042,7 +1044,15 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                                     } else {
 #pragma unroll
                                         for (int b = 0; b < NS; ++b)
+#ifdef SDPCS_I8_ABL_STS
+                                        {    // ablation (trace builds): the arithmetic stays, the stores (practically) never execute
+                                            uint32_t ka = keep[0][b], wa = w[b];
+                                            asm volatile("" : "+r"(ka), "+r"(wa));
+                                            if ((ka ^ wa) == 0xdeadbeefu) *reinterpret_cast<uint2*>(abuf + b * (I8_M * 64) + (gp >> 1) * 8) = make_uint2(ka, wa);
+                                        }
+#else
                                             *reinterpret_cast<uint2*>(abuf + b * (I8_M * 64) + (gp >> 1) * 8) = make_uint2(keep[0][b], w[b]);
+#endif
                                     }
                                 }
                             }
@@ -1069,7 +1079,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                     if (l < NHID - 1) body(std::false_type{});
                     else body(std::true_type{});
                     if (l < NHID - 1) {
+#ifndef SDPCS_I8_ABL_FENCE
                         fence_async_smem();
+#endif
                         __syncwarp();
                         if constexpr (D == 0) nb_arrive(I8_NB_ACT + ln);
                         else if (lane == 0) mbar_arrive(B_ACT + 8 * ln);

@@ -53,7 +53,7 @@ def main():
     t = t - base
     ep = t[:16]
     mma = t[16]
-    np.save(os.path.join(ROOT, "gpurun_out", "i8_trace.npy"), t)
+    np.save(os.path.join(ROOT, "gpurun_out", "i8_trace_screen.npy" if "--screen" in sys.argv else "i8_trace.npy"), t)
     if "-q" not in sys.argv:
       print("step |  MMA: start  opnd_ok  acc_free  issued | EPI: full_min full_max | empty_min empty_max | end_min end_max | wait_full(avg) busy(avg)")
     for s in range(ns if "-q" not in sys.argv else 0):
@@ -72,6 +72,16 @@ def main():
     print("MMA issue -> accumulators visible: mean %.0f  min %d  max %d cycles" % (dur.mean(), dur.min(), dur.max()))
     lag = mma[8:88, 2] - np.maximum(mma[8:88, 1], mma[8:88, 0])
     print("MMA warp waits for the accumulator hand-back (after operands are ready): mean %.0f cycles" % lag.mean())
+    # by position in the schedule: step mod 8 = 2 * layer + lane for NHID = 4 (two tiles in flight, four tansig layers each)
+    d = np.diff(ep[:, :, 0], axis=1)
+    for r in range(8):
+        sel = [s for s in range(8, 88) if s % 8 == r]
+        print("step mod 8 = %d: step %5.0f (slowest warp %5.0f) | wait %5.0f  phase 1 %5.0f  phase 2 %5.0f | issuer: operands %5.0f  hand-back %5.0f  issue %5.0f"
+              % (r, d[:, sel].mean(), d[:, sel].mean(axis=1).max(), (ep[:, sel, 1] - ep[:, sel, 0]).mean(), (ep[:, sel, 2] - ep[:, sel, 1]).mean(),
+                 (ep[:, sel, 3] - ep[:, sel, 2]).mean(), (mma[sel, 1] - mma[sel, 0]).mean(), (mma[sel, 2] - mma[sel, 1]).mean(),
+                 (mma[sel, 3] - mma[sel, 2]).mean()))
+    sp = ep[:, 8:88, 0].max(axis=0) - ep[:, 8:88, 0].min(axis=0)
+    print("spread of the step starts across the 16 warps: mean %.0f max %.0f" % (sp.mean(), sp.max()))
     for w in range(16):
         print("warp %2d (q %d cq %d): busy %.0f  wait %.0f" % (w, w & 3, w >> 2, (st[w, :, 3] - st[w, :, 1]).mean(), (st[w, :, 1] - st[w, :, 0]).mean()))
 
