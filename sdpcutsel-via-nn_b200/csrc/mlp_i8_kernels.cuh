@@ -525,6 +525,75 @@ struct I8RecombineSide {
     }
 };
 
+// The same recombination in two parts (NS = 7): the integer part -- the two pre-biased int64 words -- and the FP64 part.
+// While the tensor core executes tcgen05.mma, FP64 instructions and shared-memory loads of the SM get ~8 % of their
+// throughput (tools/tc_fp64_overlap.cu) but integer arithmetic runs at full speed: the epilogue keeps the stretch right
+// after the accumulator hand-back (when the MMAs of the other tile start) free of FP64 work.  Same operations, same
+// order as i8_recombine<7>: bit-identical results.
+template <int NS>
+__device__ __forceinline__ void i8_recombine_int7(const uint32_t (&v)[NS][8], int j, long long& accH, long long& accL)
+{
+    accH = I8_MAGIC52_BITS; accL = I8_MAGIC52_BITS;
+    if constexpr (NS == 7) {      // (only called for NS = 7; a template so that the other instances of the kernel still compile)
+        accH = (long long)(int)v[0][j] * 65536ll + accH;
+        accH = (long long)(int)v[1][j] * 256ll + accH;
+        accH = (long long)(int)v[2][j] * 1ll + accH;
+        accL = (long long)(int)v[3][j] * 16777216ll + accL;
+        accL = (long long)(int)v[4][j] * 65536ll + accL;
+        accL = (long long)(int)v[5][j] * 256ll + accL;
+        accL = (long long)(int)v[6][j] * 1ll + accL;
+    }
+}
+__device__ __forceinline__ double i8_recombine_fin7(long long accH, long long accL, double2 cb)
+{
+    const double dl = __longlong_as_double(accL) - I8_MAGIC52;
+    const double dh = __longlong_as_double(accH) - I8_MAGIC52;
+    return fma(fma(dh, 4294967296.0, dl), cb.x, cb.y);
+}
+// side work: recombination of outputs JB .. JB + 3 of the batch in v into z[ZB ..], one per stage
+template <int NS, int JB, int ZB, int NZ>
+struct I8RecombineSideAt {
+    const uint32_t (&v)[NS][8];
+    const double2* cb;          // parameters of output JB
+    double (&z)[NZ];
+    __device__ __forceinline__ I8RecombineSideAt(const uint32_t (&vv)[NS][8], const double2* c, double (&zz)[NZ]) : v(vv), cb(c), z(zz) {}
+    template <int K>
+    __device__ __forceinline__ void operator()(i8_stage<K>)
+    {
+        if constexpr (K < 4) z[ZB + K] = i8_recombine<NS>(v, JB + K, cb[K]);
+    }
+};
+// integer part of the digit slicing of four activations whose quantisation FMA (qd = fma(a, scale, 1.5 * 2^52)) is done:
+// stages 1..5 of I8SliceSide
+template <int NS>
+__device__ __forceinline__ void i8_slice_from_qd(const double (&qd)[4], uint32_t (&w)[NS])
+{
+    uint32_t lo[4], hi[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t l32 = (uint32_t)__double2loint(qd[i]), h32 = (uint32_t)__double2hiint(qd[i]) - 0x43380000u;
+        lo[i] = l32 << 3;
+        hi[i] = __funnelshift_l(l32, h32, 3);
+    }
+    {
+        const uint32_t a01 = __byte_perm(lo[0], lo[1], 0x5140), b01 = __byte_perm(lo[0], lo[1], 0x7362);
+        const uint32_t a23 = __byte_perm(lo[2], lo[3], 0x5140), b23 = __byte_perm(lo[2], lo[3], 0x7362);
+        w[NS - 1] = __byte_perm(a01, a23, 0x5410);
+        w[NS - 2] = __byte_perm(a01, a23, 0x7632);
+        w[NS - 3] = __byte_perm(b01, b23, 0x5410);
+        w[NS - 4] = __byte_perm(b01, b23, 0x7632);
+    }
+    if constexpr (NS > 4) {
+        const uint32_t a01 = __byte_perm(hi[0], hi[1], 0x5140), a23 = __byte_perm(hi[2], hi[3], 0x5140);
+        w[NS - 5] = __byte_perm(a01, a23, 0x5410);
+        if constexpr (NS > 5) w[NS - 6] = __byte_perm(a01, a23, 0x7632);
+        if constexpr (NS > 6) {
+            const uint32_t b01 = __byte_perm(hi[0], hi[1], 0x7362), b23 = __byte_perm(hi[2], hi[3], 0x7362);
+            w[NS - 7] = __byte_perm(b01, b23, 0x5410);
+        }
+    }
+}
+
 // Write one row (candidate) of a layer-0 tile image: NIN mapminmax'ed inputs -> NS slices x 32 digit bytes, plus aux.
 // Shared-memory image: [slice s (0 = most significant)][k chunk c = k / 16][row][k % 16]; staged tile: see I8Dig::TILE_BYTES.
 template <int NIN, int NS>
@@ -983,6 +1052,98 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                     uint8_t* abuf = sm + L::OFF_A + ln * G::AH_BYTES + cq * (I8_M * 16) + row * 16;
                     constexpr bool WIDE_STORE = (NS <= 4);   // 7 digits: three groups of pending words would spill (measured: +6 % step time)
                     double part = 0.0;
+                    // NS = 7 (one accumulator stage): the MMAs of the other tile start at the hand-back, and while they run the FP64
+                    // pipe and the shared-memory loads of the SM all but stand still (tools/tc_fp64_overlap.cu).  The step is therefore
+                    // ordered FP64 | hand-back | integer | FP64: the first eight outputs go through tansig BEFORE the hand-back,
+                    // the stretch after it holds integer work only (slicing and stores of the first eight activations, integer
+                    // recombination of the last eight accumulators), the FP64 work of the last eight outputs follows.
+                    auto body7 = [&](auto last_tag) {
+                        constexpr bool LAST = decltype(last_tag)::value;
+                        double z[8], act0[4], act1[4];
+                        uint32_t v[NS][8];
+#pragma unroll
+                        for (int dg = 0; dg < NS; ++dg) tmem_ld8_async(tbase + dg * I8_N, v[dg]);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) z[j] = i8_recombine<NS>(v, j, csbs[j]);
+                        {
+                            double zz[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) zz[i] = z[i];
+                            tansig4_woven(zz, act0, tab, I8RecombineSideAt<NS, 4, 4, 8>(v, csbs + 4, z));
+                        }
+                        uint32_t keep[NS], w[NS];
+                        double qd1[4];
+                        if constexpr (!LAST) {
+                            double zz[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) zz[i] = z[4 + i];
+                            tansig4_woven(zz, act1, tab, I8SliceSide<NS>(act0, G::SCALE_H, keep));
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) qd1[i] = fma(act1[i], G::SCALE_H, I8_MAGIC52);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) part = fma(wout[i], act0[i], part);
+                            double zz[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) zz[i] = z[4 + i];
+                            tansig4_woven(zz, act1, tab, I8NoSide());
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) part = fma(wout[4 + i], act1[i], part);
+                        }
+#pragma unroll
+                        for (int dg = 0; dg < NS; ++dg) tmem_ld8_async(tbase + dg * I8_N + 8, v[dg]);
+                        tmem_wait_ld();
+                        tc_fence_before();
+                        __syncwarp();
+                        if constexpr (D == 0) nb_arrive(I8_NB_EMPTY + st);
+                        else mbar_arrive_lane0(B_EMPTY + 8 * st, lane);
+#ifdef SDPCS_I8_EPISYNC
+                        asm volatile("bar.sync 7, 512;" ::: "memory");      // all 16 epilogue warps enter the MMA window together
+#endif
+                        I8_STAMP(step, 2);
+                        // ---- integer only: the tensor core is busy with the other tile
+                        if constexpr (!LAST) {
+                            i8_slice_from_qd<NS>(qd1, w);
+#pragma unroll
+                            for (int b = 0; b < NS; ++b) *reinterpret_cast<uint2*>(abuf + b * (I8_M * 64)) = make_uint2(keep[b], w[b]);
+                        }
+                        long long aH[8], aL[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) i8_recombine_int7(v, j, aH[j], aL[j]);
+                        // ---- FP64 again (program order: the conversions need the integer words above)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) z[j] = i8_recombine_fin7(aH[j], aL[j], csbs[8 + j]);
+                        {
+                            double zz[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) zz[i] = z[i];
+                            tansig4_woven(zz, act0, tab, I8NoSide());
+                        }
+                        if constexpr (!LAST) {
+                            double zz[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) zz[i] = z[4 + i];
+                            tansig4_woven(zz, act1, tab, I8SliceSide<NS>(act0, G::SCALE_H, keep));
+                            unsigned long long u[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) u[i] = i8_quantize(act1[i], G::SCALE_H);
+                            i8_pack_slices<NS>(u[0], u[1], u[2], u[3], w);
+#pragma unroll
+                            for (int b = 0; b < NS; ++b) *reinterpret_cast<uint2*>(abuf + b * (I8_M * 64) + 8) = make_uint2(keep[b], w[b]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) part = fma(wout[8 + i], act0[i], part);
+                            double zz[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) zz[i] = z[4 + i];
+                            tansig4_woven(zz, act1, tab, I8NoSide());
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) part = fma(wout[12 + i], act1[i], part);
+                        }
+                    };
+                    // NS = 4 (two accumulator stages: the MMAs are not tied to the hand-back) and the debug instance (which dumps all
+                    // sixteen pre-activations of a layer): the order of round 2's first half -- same arithmetic
                     auto body = [&](auto last_tag) {
                         constexpr bool LAST = decltype(last_tag)::value;
                         double z[16];
@@ -1076,8 +1237,16 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                             }
                         }
                     };
-                    if (l < NHID - 1) body(std::false_type{});
-                    else body(std::true_type{});
+#ifndef SDPCS_I8_OLD_ORDER
+                    if constexpr (NS == 7 && !DBG) {
+                        if (l < NHID - 1) body7(std::false_type{});
+                        else body7(std::true_type{});
+                    } else
+#endif
+                    {
+                        if (l < NHID - 1) body(std::false_type{});
+                        else body(std::true_type{});
+                    }
                     if (l < NHID - 1) {
 #ifndef SDPCS_I8_ABL_FENCE
                         fence_async_smem();
