@@ -290,11 +290,7 @@ __device__ __forceinline__ void tansig_scaled_vec(const double (&zs)[W], double 
     for (int i = 0; i < W; ++i) q[i] = q[i] * s[i];
 #pragma unroll
     for (int i = 0; i < W; ++i) {
-#ifdef SDPCS_I8_ABL_TAB
-        const double Tj = T[0];          // ablation (trace builds): no table look-up traffic, wrong values
-#else
         const double Tj = T[idx[i] & 255];
-#endif
         const double t0 = fma(Tj, q[i], Tj);
         t[i] = __hiloint2double(__double2hiint(t0) + (int)((uint32_t)(idx[i] & ~255) << 12), __double2loint(t0));
     }
@@ -404,13 +400,7 @@ __device__ __forceinline__ void tansig4_woven(const double (&zs)[4], double (&ou
     side(i8_stage<4>{});
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-#if defined(SDPCS_I8_ABL_TAB) && SDPCS_I8_ABL_TAB == 2
-        const double Tj = 1.0 + 0.001 * (double)(idx[i] & 255);   // ablation (trace builds): no load at all, wrong values
-#elif defined(SDPCS_I8_ABL_TAB)
-        const double Tj = T[0];          // ablation (trace builds): no table look-up traffic, wrong values
-#else
         const double Tj = T[idx[i] & 255];
-#endif
         const double t0 = fma(Tj, q[i], Tj);
         t[i] = __hiloint2double(__double2hiint(t0) + (int)((uint32_t)(idx[i] & ~255) << 12), __double2loint(t0));
     }
@@ -1038,9 +1028,6 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                     if (!ok) break;
                     I8_STAMP(step, 1);
                     tc_fence_after();
-#ifdef SDPCS_I8_QSYNC
-                    if ((step & (SDPCS_I8_QSYNC - 1)) == 0) quarter_sync(q);
-#endif
                     const double2* csbs = reinterpret_cast<const double2*>(par + L::P_CS) + l * 64 + cq * 16;   // (cs, bs) pairs
                     const double* wout = par + L::P_WOUT + cq * 16;
                     // Phase 1: read the NS diagonals (two batches of TMEM loads, 8 neurons each), recombine them exactly in int64 and
@@ -1098,9 +1085,6 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                         __syncwarp();
                         if constexpr (D == 0) nb_arrive(I8_NB_EMPTY + st);
                         else mbar_arrive_lane0(B_EMPTY + 8 * st, lane);
-#ifdef SDPCS_I8_EPISYNC
-                        asm volatile("bar.sync 7, 512;" ::: "memory");      // all 16 epilogue warps enter the MMA window together
-#endif
                         I8_STAMP(step, 2);
                         // ---- integer only: the tensor core is busy with the other tile
                         if constexpr (!LAST) {
@@ -1205,15 +1189,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                                     } else {
 #pragma unroll
                                         for (int b = 0; b < NS; ++b)
-#ifdef SDPCS_I8_ABL_STS
-                                        {    // ablation (trace builds): the arithmetic stays, the stores (practically) never execute
-                                            uint32_t ka = keep[0][b], wa = w[b];
-                                            asm volatile("" : "+r"(ka), "+r"(wa));
-                                            if ((ka ^ wa) == 0xdeadbeefu) *reinterpret_cast<uint2*>(abuf + b * (I8_M * 64) + (gp >> 1) * 8) = make_uint2(ka, wa);
-                                        }
-#else
                                             *reinterpret_cast<uint2*>(abuf + b * (I8_M * 64) + (gp >> 1) * 8) = make_uint2(keep[0][b], w[b]);
-#endif
                                     }
                                 }
                             }
@@ -1237,20 +1213,16 @@ __global__ void __launch_bounds__(I8_THREADS, 1) k_mlp_i8(MlpI8Args a)
                             }
                         }
                     };
-#ifndef SDPCS_I8_OLD_ORDER
                     if constexpr (NS == 7 && !DBG) {
                         if (l < NHID - 1) body7(std::false_type{});
                         else body7(std::true_type{});
                     } else
-#endif
                     {
                         if (l < NHID - 1) body(std::false_type{});
                         else body(std::true_type{});
                     }
                     if (l < NHID - 1) {
-#ifndef SDPCS_I8_ABL_FENCE
                         fence_async_smem();
-#endif
                         __syncwarp();
                         if constexpr (D == 0) nb_arrive(I8_NB_ACT + ln);
                         else if (lane == 0) mbar_arrive(B_ACT + 8 * ln);
