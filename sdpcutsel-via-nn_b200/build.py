@@ -15,7 +15,7 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(PKG, "csrc", f) for f in os.listdir(os.path.join(PKG, "csrc"))]
+    deps = [os.path.join(PKG, "csrc", f) for f in os.listdir(os.path.join(PKG, "csrc")) if f.endswith((".cu", ".cuh", ".h"))]
     deps.append(os.path.join(os.path.dirname(PKG), "include", "sdpcutsel.h"))
     return any(os.path.getmtime(d) > t for d in deps)
 
