@@ -14,7 +14,7 @@ using namespace sdpcs;
 
 constexpr int SMEM = 96 * 1024;
 
-__global__ void __launch_bounds__(544, 1) k_overlap(int n_mma, int math_mode, int n_math, int nw_math, long long* out, double* sink)
+__global__ void __launch_bounds__(544, 1) k_overlap(int n_mma, int math_mode, int n_math, int nw_math, long long* out, double* sink, int gap = 0)
 {
     extern __shared__ __align__(1024) uint8_t sm[];
     __shared__ uint64_t bar;
@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(544, 1) k_overlap(int n_mma, int math_mode, in
                 __syncwarp();
                 while (!mbar_try_hint(b, phase, 20000u)) { if (clock64() - t0 > 4000000000ll) break; }     // never hang the box
                 phase ^= 1;
+                if (gap > 0) { const long long tg = clock64(); while (clock64() - tg < gap) {} }              // idle tensor core between the steps
             }
             t1 = clock64();
         }
@@ -164,6 +165,34 @@ int main()
             run(n_mma, mode, n_math, nw, t_mma_with, t_with);
             printf("%2d warps of %-30s: alone %9.0f cycles, with MMAs %9.0f (x%.3f) | MMA stream: alone %9.0f, with the math %9.0f (x%.3f)\n", nw, names[mode],
                    t_alone, t_with, t_with / t_alone, tm0, t_mma_with, t_mma_with / tm0);
+        }
+    }
+    // duty cycle: the same MMA steps with idle gaps between them; FP64 work sized to the MMA stream alone (no gaps)
+    printf("\nFP64 DFMA (16 warps) next to MMA steps separated by idle gaps (one step = 14 MMAs, ~2,000 cycles):\n");
+    {
+        int n_math = 2000;
+        double t_alone, d2;
+        run(0, 1, n_math, 16, d2, t_alone);
+        n_math = (int)(n_math * (tm0 / t_alone));
+        run(0, 1, n_math, 16, d2, t_alone);
+        for (int gap : {0, 1000, 2000, 4000, 8000}) {
+            for (int rep = 0; rep < 2; ++rep) {
+                cudaMemset(d_out, 0, sizeof(long long) * sms * 17);
+                k_overlap<<<sms, 544, SMEM>>>(n_mma, 1, n_math, 16, d_out, d_sink, gap);
+                cudaDeviceSynchronize();
+            }
+            cudaMemcpy(h.data(), d_out, sizeof(long long) * sms * 17, cudaMemcpyDeviceToHost);
+            double a = 0, m = 0;
+            for (int s = 0; s < sms; ++s) {
+                a += (double)h[s * 17 + 16];
+                double mx = 0;
+                for (int w = 0; w < 16; ++w) mx = std::max(mx, (double)h[s * 17 + w]);
+                m += mx;
+            }
+            a /= sms; m /= sms;
+            const double duty = tm0 / a;      // share of the time the tensor core is busy
+            printf("  gap %5d cycles: MMA stream %9.0f cycles (tensor core busy %.0f %% of it), FP64 work %9.0f cycles (alone %9.0f): FP64 throughput while both run = %.0f %% of alone\n",
+                   gap, a, 100 * duty, m, t_alone, m <= a ? 100.0 * t_alone / m : 100.0 * (t_alone - (m - a)) / a);
         }
     }
     return 0;
