@@ -146,3 +146,26 @@ def test_mixin_composition_with_the_reference_classes():
     assert ref.CutSolver._THRES_MAX_SUBS == B._THRES_MAX_SUBS == 2 ** 44
     g = G()
     assert g._Mat[0].shape == (3, 3) and g._blobs == {}          # both __init__ ran
+
+
+def test_rank_list_seal_detects_any_change():
+    """RankList._sealed_rows (cut_select_qp.py mirror): the arrays behind the entries are only handed out while the list
+    holds exactly the entries it was returned with -- _gen_eigcuts_selected walks the entries otherwise."""
+    RankList = pkg.cut_select_qp.RankList
+    rows, scores = np.arange(12, dtype=np.int16).reshape(4, 3), np.array([4.0, 3.0, 2.0, 1.0])
+    rl = RankList([([0, 1, 2], 4.0), ([3, 4, 5], 3.0), ([6, 7, 8], 2.0), ([9, 10, 11], 1.0)])
+    assert rl._sealed_rows() is None                      # never sealed
+    rl._seal(rows, scores)
+    got = rl._sealed_rows()
+    assert got is not None and got[0] is rows and got[1] is scores
+    assert list(rl)._sealed_rows() is None if hasattr(list(rl), "_sealed_rows") else True   # a copy is a plain list
+    for change in (lambda l: l.reverse(), lambda l: l.pop(), lambda l: l.append(([1], 0.0)),
+                   lambda l: l.__setitem__(1, ([3, 4, 5], 3.0)), lambda l: l.sort(key=lambda e: e[1])):
+        cp = RankList(rl)
+        cp._seal(rows, scores)
+        assert cp._sealed_rows() is not None
+        change(cp)
+        assert cp._sealed_rows() is None
+    empty = RankList()
+    empty._seal(np.zeros((0, 3), np.int16), np.zeros(0))
+    assert empty._sealed_rows() is not None
